@@ -1,0 +1,497 @@
+"""Detector error model (DEM): container, circuit -> DEM analysis, graphlike decomposition, text IO.
+
+This is the host-side (setup-time) stage in front of the CUDA hot path.  It restates what sinter
+asks Stim for when ``ThresholdLAB`` hands it a ``Task`` without a DEM
+(``/root/reference/graphqec/lab/threshold/threshold_lab.py:151,182-197``):
+``circuit.detector_error_model(decompose_errors=True, approximate_disjoint_errors=True)`` with a
+fallback to the undecomposed model when decomposition fails.
+
+Analysis method (restated, not Stim's code): walk the circuit backwards keeping, for every qubit,
+the set of detectors/observables an X or a Z inserted at that point would flip; every Pauli
+component of every noise channel then reads its symptom set off that table.  Sets are Python ints
+used as bit masks (bit d = detector d, bit D+o = observable o).
+"""
+
+from __future__ import annotations
+
+import itertools
+import math
+import re
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from graphqec_b200.circuit import Circuit, GateTarget
+
+__all__ = ["DetectorErrorModel", "circuit_to_dem", "depolarize1_component", "depolarize2_component"]
+
+NO_DET = 0xFFFFFFFF
+
+
+def depolarize1_component(p: float) -> float:
+    """Probability of each of the 3 independent Pauli components equivalent to DEPOLARIZE1(p)."""
+    if p > 0.75:
+        raise ValueError("DEPOLARIZE1 probability above 3/4 has no independent-component form")
+    return 0.5 - 0.5 * math.sqrt(1.0 - 4.0 * p / 3.0)
+
+
+def depolarize2_component(p: float) -> float:
+    """Probability of each of the 15 independent Pauli components equivalent to DEPOLARIZE2(p)."""
+    if p > 15.0 / 16.0:
+        raise ValueError("DEPOLARIZE2 probability above 15/16 has no independent-component form")
+    return 0.5 - 0.5 * (1.0 - 16.0 * p / 15.0) ** 0.125
+
+
+def _xor_prob(p1: float, p2: float) -> float:
+    return p1 * (1.0 - p2) + p2 * (1.0 - p1)
+
+
+def _bits(mask: int) -> list[int]:
+    out = []
+    while mask:
+        low = mask & -mask
+        out.append(low.bit_length() - 1)
+        mask ^= low
+    return out
+
+
+class DetectorErrorModel:
+    """Independent error mechanisms ``(probability, detector set, observable set)`` in CSR form.
+
+    ``components`` (optional) lists, per mechanism, its graphlike pieces as
+    ``(det_a, det_b or NO_DET, observable mask)`` -- what Stim prints as ``D.. ^ D..`` -- and is what
+    the matching decoder builds its graph from (PyMatching ignores pieces with more than two
+    detectors).
+    """
+
+    def __init__(
+        self,
+        num_detectors: int,
+        num_observables: int,
+        probs: Sequence[float],
+        dets: Sequence[Sequence[int]],
+        obs: Sequence[Sequence[int]],
+        components: Sequence[Sequence[tuple[int, int, int]]] | None = None,
+    ) -> None:
+        self.num_detectors = int(num_detectors)
+        self.num_observables = int(num_observables)
+        self.probs = np.asarray(probs, dtype=np.float64).reshape(-1)
+        m = self.probs.shape[0]
+        if len(dets) != m or len(obs) != m:
+            raise ValueError("probs / dets / obs must have one entry per mechanism")
+        self.det_indptr = np.zeros(m + 1, dtype=np.uint32)
+        self.obs_indptr = np.zeros(m + 1, dtype=np.uint32)
+        if m:
+            self.det_indptr[1:] = np.cumsum([len(d) for d in dets])
+            self.obs_indptr[1:] = np.cumsum([len(o) for o in obs])
+        self.det_idx = np.fromiter(
+            itertools.chain.from_iterable(dets), dtype=np.uint32, count=int(self.det_indptr[-1])
+        )
+        self.obs_idx = np.fromiter(
+            itertools.chain.from_iterable(obs), dtype=np.uint32, count=int(self.obs_indptr[-1])
+        )
+        if self.det_idx.size and int(self.det_idx.max()) >= self.num_detectors:
+            raise ValueError("detector index out of range")
+        if self.obs_idx.size and int(self.obs_idx.max()) >= self.num_observables:
+            raise ValueError("observable index out of range")
+        if np.any(self.probs < 0) or np.any(self.probs > 1):
+            raise ValueError("mechanism probability out of [0, 1]")
+        self.decomposed = components is not None
+        if components is None:
+            components = [
+                [self._self_component(i)] for i in range(m)
+            ]
+        self.comp_indptr = np.zeros(m + 1, dtype=np.uint32)
+        if m:
+            self.comp_indptr[1:] = np.cumsum([len(c) for c in components])
+        flat = list(itertools.chain.from_iterable(components))
+        self.comp_a = np.array([c[0] for c in flat], dtype=np.uint32)
+        self.comp_b = np.array([c[1] for c in flat], dtype=np.uint32)
+        self.comp_obs = np.array([c[2] for c in flat], dtype=np.uint64)
+
+    # ------------------------------------------------------------------ helpers
+    def _self_component(self, i: int) -> tuple[int, int, int]:
+        d = self.det_idx[self.det_indptr[i] : self.det_indptr[i + 1]]
+        omask = 0
+        for o in self.obs_idx[self.obs_indptr[i] : self.obs_indptr[i + 1]]:
+            omask |= 1 << int(o)
+        if len(d) == 1:
+            return (int(d[0]), NO_DET, omask)
+        if len(d) == 2:
+            return (int(d[0]), int(d[1]), omask)
+        # 0 detectors or a hyperedge: not graphlike -> marked with both ends absent (ignored by
+        # the matching-graph builder, sampled all the same).
+        return (NO_DET, NO_DET, omask)
+
+    @property
+    def num_errors(self) -> int:
+        return int(self.probs.shape[0])
+
+    @property
+    def nnz(self) -> int:
+        return int(self.det_idx.shape[0])
+
+    def mechanism(self, i: int) -> tuple[float, tuple[int, ...], tuple[int, ...]]:
+        d = self.det_idx[self.det_indptr[i] : self.det_indptr[i + 1]]
+        o = self.obs_idx[self.obs_indptr[i] : self.obs_indptr[i + 1]]
+        return float(self.probs[i]), tuple(int(x) for x in d), tuple(int(x) for x in o)
+
+    def mechanism_components(self, i: int) -> list[tuple[int, int, int]]:
+        s, e = int(self.comp_indptr[i]), int(self.comp_indptr[i + 1])
+        return [(int(self.comp_a[k]), int(self.comp_b[k]), int(self.comp_obs[k])) for k in range(s, e)]
+
+    def graphlike_components(self) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """Flat list of graphlike pieces ``(a, b|NO_DET, obs mask, probability of the parent)``."""
+        reps = np.diff(self.comp_indptr.astype(np.int64))
+        p = np.repeat(self.probs, reps)
+        keep = self.comp_a != NO_DET
+        return self.comp_a[keep], self.comp_b[keep], self.comp_obs[keep], p[keep]
+
+    def dense_check_matrices(self) -> tuple[np.ndarray, np.ndarray]:
+        """Dense uint8 H (D x M) and L (O x M); only for small models / tests."""
+        h = np.zeros((self.num_detectors, self.num_errors), dtype=np.uint8)
+        l = np.zeros((self.num_observables, self.num_errors), dtype=np.uint8)
+        for i in range(self.num_errors):
+            h[self.det_idx[self.det_indptr[i] : self.det_indptr[i + 1]], i] = 1
+            l[self.obs_idx[self.obs_indptr[i] : self.obs_indptr[i + 1]], i] = 1
+        return h, l
+
+    def summary(self) -> dict:
+        sizes = np.diff(self.det_indptr.astype(np.int64))
+        hist = {int(k): int(v) for k, v in zip(*np.unique(sizes, return_counts=True))}
+        return {
+            "D": self.num_detectors,
+            "O": self.num_observables,
+            "M": self.num_errors,
+            "nnz_H": self.nnz,
+            "nnz_L": int(self.obs_idx.shape[0]),
+            "sum_p": float(self.probs.sum()),
+            "min_p": float(self.probs.min()) if self.num_errors else 0.0,
+            "max_p": float(self.probs.max()) if self.num_errors else 0.0,
+            "distinct_p": int(np.unique(self.probs).shape[0]),
+            "dets_per_mechanism": hist,
+        }
+
+    # ------------------------------------------------------------------ text IO (Stim .dem syntax)
+    def __str__(self) -> str:
+        lines = []
+        for i in range(self.num_errors):
+            p, d, o = self.mechanism(i)
+            if self.decomposed:
+                parts = []
+                for a, b, om in self.mechanism_components(i):
+                    toks = [f"D{x}" for x in (a, b) if x != NO_DET] + [f"L{x}" for x in _bits(om)]
+                    parts.append(" ".join(toks))
+                if parts == [""] or any(a == NO_DET and b == NO_DET for a, b, _ in self.mechanism_components(i)):
+                    parts = [" ".join([f"D{x}" for x in d] + [f"L{x}" for x in o])]
+                body = " ^ ".join(parts)
+            else:
+                body = " ".join([f"D{x}" for x in d] + [f"L{x}" for x in o])
+            lines.append(f"error({p!r}) {body}".rstrip())
+        if self.num_detectors:
+            covered = int(self.det_idx.max()) + 1 if self.det_idx.size else 0
+            if covered < self.num_detectors:
+                lines.append(f"detector D{self.num_detectors - 1}")
+        if self.num_observables:
+            covered = int(self.obs_idx.max()) + 1 if self.obs_idx.size else 0
+            if covered < self.num_observables:
+                lines.append(f"logical_observable L{self.num_observables - 1}")
+        return "\n".join(lines)
+
+    @staticmethod
+    def from_text(text: str) -> "DetectorErrorModel":
+        """Parse Stim's .dem syntax: error / detector / logical_observable / shift_detectors / repeat."""
+        lines = _flatten_dem_lines(text)
+        probs, dets, obs, comps = [], [], [], []
+        any_sep = False
+        nd = no = 0
+        shift = 0
+        for kind, arg, toks in lines:
+            if kind == "shift_detectors":
+                shift += int(toks[0]) if toks else 0
+                continue
+            if kind == "detector":
+                for t in toks:
+                    if t.startswith("D"):
+                        nd = max(nd, int(t[1:]) + shift + 1)
+                continue
+            if kind == "logical_observable":
+                for t in toks:
+                    if t.startswith("L"):
+                        no = max(no, int(t[1:]) + 1)
+                continue
+            if kind != "error":
+                raise ValueError(f"unsupported DEM instruction: {kind}")
+            dset: set[int] = set()
+            oset: set[int] = set()
+            pieces = []
+            cur_d: list[int] = []
+            cur_o = 0
+            for t in toks + ["^"]:
+                if t == "^":
+                    a = cur_d[0] if len(cur_d) >= 1 else NO_DET
+                    b = cur_d[1] if len(cur_d) == 2 else NO_DET
+                    if len(cur_d) > 2:
+                        a = b = NO_DET
+                    pieces.append((a, b, cur_o))
+                    cur_d, cur_o = [], 0
+                    continue
+                if t.startswith("D"):
+                    k = int(t[1:]) + shift
+                    nd = max(nd, k + 1)
+                    dset ^= {k}
+                    cur_d.append(k)
+                elif t.startswith("L"):
+                    k = int(t[1:])
+                    no = max(no, k + 1)
+                    oset ^= {k}
+                    cur_o ^= 1 << k
+                else:
+                    raise ValueError(f"bad DEM target {t!r}")
+            if len(pieces) > 1:
+                any_sep = True
+            probs.append(float(arg))
+            dets.append(sorted(dset))
+            obs.append(sorted(oset))
+            comps.append(pieces)
+        return DetectorErrorModel(nd, no, probs, dets, obs, comps if any_sep else None)
+
+
+_DEM_LINE = re.compile(r"^([a-z_]+)\s*(?:\(([^)]*)\))?\s*(.*)$")
+
+
+def _flatten_dem_lines(text: str) -> list[tuple[str, str | None, list[str]]]:
+    """Expand ``repeat N { ... }`` blocks (detector shifts are applied by the caller in order)."""
+    raw = [ln.split("#", 1)[0].strip() for ln in text.splitlines()]
+    raw = [ln for ln in raw if ln]
+
+    def parse(block: list[str], pos: int) -> tuple[list, int]:
+        out = []
+        while pos < len(block):
+            ln = block[pos]
+            if ln == "}":
+                return out, pos + 1
+            if ln.startswith("repeat"):
+                count = int(ln.split()[1])
+                body, pos = parse(block, pos + 1)
+                for _ in range(count):
+                    out.extend(body)
+                continue
+            m = _DEM_LINE.match(ln)
+            if not m:
+                raise ValueError(f"cannot parse DEM line {ln!r}")
+            out.append((m.group(1), m.group(2), m.group(3).split()))
+            pos += 1
+        return out, pos
+
+    return parse(raw, 0)[0]
+
+
+# --------------------------------------------------------------------------------------------
+# circuit -> DEM
+# --------------------------------------------------------------------------------------------
+
+def _measurement_masks(circuit: Circuit) -> list[int]:
+    """mask[m] = detectors/observables whose record list holds measurement m an odd number of times."""
+    nmeas = circuit.num_measurements
+    nd = circuit.num_detectors
+    masks = [0] * nmeas
+    seen = 0
+    det = 0
+    for op in circuit:
+        kind = op.kind
+        if kind in ("measure", "measure_reset"):
+            seen += len(op.targets)
+        elif op.name == "DETECTOR":
+            for t in op.targets:
+                masks[seen + t.value] ^= 1 << det
+            det += 1
+        elif op.name == "OBSERVABLE_INCLUDE":
+            bit = 1 << (nd + int(op.gate_args[0]))
+            for t in op.targets:
+                masks[seen + t.value] ^= bit
+    return masks
+
+
+def analyze_circuit_errors(circuit: Circuit) -> dict[int, float]:
+    """Symptom mask -> probability for every independent error mechanism of the circuit."""
+    masks = _measurement_masks(circuit)
+    nq = circuit.num_qubits
+    xs = [0] * nq  # symptom of an X inserted here
+    zs = [0] * nq  # symptom of a Z inserted here
+    m = circuit.num_measurements
+    out: dict[int, float] = {}
+
+    def emit(mask: int, p: float) -> None:
+        if mask == 0 or p <= 0.0:
+            return
+        old = out.get(mask)
+        out[mask] = p if old is None else _xor_prob(old, p)
+
+    for op in reversed(circuit._ops):
+        name, kind, t = op.name, op.kind, op.targets
+        if kind == "annotation":
+            continue
+        if kind == "noise1":
+            p = op.gate_args[0] if op.gate_args else 0.0
+            if name == "DEPOLARIZE1":
+                q1 = depolarize1_component(p)
+                for q in t:
+                    emit(xs[q], q1)
+                    emit(zs[q], q1)
+                    emit(xs[q] ^ zs[q], q1)
+            elif name == "X_ERROR":
+                for q in t:
+                    emit(xs[q], p)
+            elif name == "Z_ERROR":
+                for q in t:
+                    emit(zs[q], p)
+            else:  # Y_ERROR
+                for q in t:
+                    emit(xs[q] ^ zs[q], p)
+        elif kind == "noise2":
+            q2 = depolarize2_component(op.gate_args[0] if op.gate_args else 0.0)
+            for k in range(0, len(t), 2):
+                a, b = t[k], t[k + 1]
+                basis = (xs[a], zs[a], xs[b], zs[b])
+                for sel in range(1, 16):
+                    mask = 0
+                    if sel & 1:
+                        mask ^= basis[0]
+                    if sel & 2:
+                        mask ^= basis[1]
+                    if sel & 4:
+                        mask ^= basis[2]
+                    if sel & 8:
+                        mask ^= basis[3]
+                    emit(mask, q2)
+        elif kind == "measure":
+            flip = op.gate_args[0] if op.gate_args else 0.0
+            for q in reversed(t):
+                m -= 1
+                if name == "M":
+                    xs[q] ^= masks[m]
+                else:
+                    zs[q] ^= masks[m]
+                emit(masks[m], flip)
+        elif kind == "measure_reset":
+            flip = op.gate_args[0] if op.gate_args else 0.0
+            for q in reversed(t):
+                m -= 1
+                if name == "MR":
+                    xs[q], zs[q] = masks[m], 0
+                else:
+                    xs[q], zs[q] = 0, masks[m]
+                emit(masks[m], flip)
+        elif kind == "reset":
+            for q in t:
+                xs[q] = 0
+                zs[q] = 0
+        elif name == "H":
+            for q in t:
+                xs[q], zs[q] = zs[q], xs[q]
+        elif name in ("S", "S_DAG"):
+            for q in t:
+                xs[q] ^= zs[q]
+        elif name == "CX":
+            for k in range(len(t) - 2, -1, -2):
+                c, x = t[k], t[k + 1]
+                xs[c] ^= xs[x]
+                zs[x] ^= zs[c]
+        elif name == "CZ":
+            for k in range(len(t) - 2, -1, -2):
+                a, b = t[k], t[k + 1]
+                xs[a] ^= zs[b]
+                xs[b] ^= zs[a]
+        elif name == "SWAP":
+            for k in range(len(t) - 2, -1, -2):
+                a, b = t[k], t[k + 1]
+                xs[a], xs[b] = xs[b], xs[a]
+                zs[a], zs[b] = zs[b], zs[a]
+        # X, Y, Z, I: Pauli gates do not move sensitivities
+    if m != 0:
+        raise AssertionError("measurement bookkeeping out of sync")
+    return out
+
+
+def _decompose(
+    dets: tuple[int, ...], omask: int, graphlike: dict[tuple[int, ...], set[int]]
+) -> list[tuple[int, int, int]] | None:
+    """Split a >2-detector symptom into graphlike pieces that exist as stand-alone mechanisms.
+
+    Fewest pieces first; the observable mask must be reproduced by the pieces' own masks.
+    """
+    best: list[tuple[int, int, int]] | None = None
+
+    def rec(rest: tuple[int, ...], acc: list[tuple[tuple[int, ...], ...]]):
+        nonlocal best
+        if best is not None and len(acc) >= len(best):
+            return
+        if not rest:
+            # choose observable masks
+            choices = [sorted(graphlike[b]) for b in acc]
+            for pick in itertools.product(*choices):
+                x = 0
+                for v in pick:
+                    x ^= v
+                if x == omask:
+                    best = [
+                        (b[0], b[1] if len(b) == 2 else NO_DET, v) for b, v in zip(acc, pick)
+                    ]
+                    return
+            return
+        a = rest[0]
+        for j in range(1, len(rest)):
+            blk = (a, rest[j])
+            if blk in graphlike:
+                rec(rest[1:j] + rest[j + 1 :], acc + [blk])
+        if (a,) in graphlike:
+            rec(rest[1:], acc + [(a,)])
+
+    rec(dets, [])
+    return best
+
+
+def circuit_to_dem(circuit: Circuit, decompose_errors: bool = False) -> DetectorErrorModel:
+    """Restatement of ``stim.Circuit.detector_error_model`` for graphqec's gate set.
+
+    With ``decompose_errors=True`` a mechanism flipping more than two detectors is rewritten as
+    graphlike pieces that already occur on their own; ``ValueError`` is raised when one cannot be
+    (sinter then falls back to the undecomposed model -- callers mirror that).
+    """
+    nd, no = circuit.num_detectors, circuit.num_observables
+    table = analyze_circuit_errors(circuit)
+    dmask = (1 << nd) - 1
+    rows = []
+    for mask, p in table.items():
+        rows.append((tuple(_bits(mask & dmask)), mask >> nd, p))
+    rows.sort(key=lambda r: (r[0], r[1]))
+    comps = None
+    if decompose_errors:
+        graphlike: dict[tuple[int, ...], set[int]] = {}
+        for d, om, _ in rows:
+            if 1 <= len(d) <= 2:
+                graphlike.setdefault(d, set()).add(om)
+        comps = []
+        for d, om, _ in rows:
+            if len(d) <= 2:
+                a = d[0] if len(d) >= 1 else NO_DET
+                b = d[1] if len(d) == 2 else NO_DET
+                comps.append([(a, b, om)])
+                continue
+            pieces = _decompose(d, om, graphlike)
+            if pieces is None:
+                raise ValueError(
+                    "Failed to decompose an error into graphlike components: "
+                    + " ".join(f"D{x}" for x in d)
+                    + "".join(f" L{x}" for x in _bits(om))
+                )
+            comps.append(pieces)
+    return DetectorErrorModel(
+        nd,
+        no,
+        [r[2] for r in rows],
+        [r[0] for r in rows],
+        [_bits(r[1]) for r in rows],
+        comps,
+    )
