@@ -1,0 +1,197 @@
+// Decoder handle, host-buffer entry point (sinter's decode_shots_bit_packed) and the fused
+// sample -> decode -> count pipeline (one sinter worker batch).
+#include <string.h>
+
+#include <algorithm>
+
+#include "gq_common.h"
+
+static void default_params(gq_decoder_params *p) {
+    memset(p, 0, sizeof(*p));
+    p->weight_levels = 1000;
+    p->bp_max_iter = 30;
+    p->bp_alpha = 0.625f;
+}
+
+extern "C" int gq_decoder_create(gq_dem *dem, int kind, const gq_decoder_params *params, gq_dec **out) {
+    if (!dem || !out) GQ_FAIL(GQ_E_INVALID, "gq_decoder_create: NULL argument");
+    *out = nullptr;
+    GQ_CUDA(cudaSetDevice(dem->device));
+    gq_dec *dec = new gq_dec();
+    dec->dem = dem;
+    dec->kind = kind;
+    default_params(&dec->params);
+    if (params) {
+        if (params->weight_levels > 0) dec->params.weight_levels = params->weight_levels;
+        dec->params.fast_capacity = params->fast_capacity;
+        dec->params.with_corrections = params->with_corrections;
+        if (params->bp_max_iter > 0) dec->params.bp_max_iter = params->bp_max_iter;
+        if (params->bp_alpha > 0) dec->params.bp_alpha = params->bp_alpha;
+    }
+    int rc;
+    if (kind == GQ_DECODER_MATCHING) rc = gq_matching_create(dec);
+    else if (kind == GQ_DECODER_BP_MINSUM) rc = gq_bp_create(dec);
+    else { delete dec; GQ_FAIL(GQ_E_INVALID, "gq_decoder_create: unknown decoder kind"); }
+    if (rc) { gq_decoder_destroy(dec); return rc; }
+    if (cudaMalloc((void **)&dec->d_count, 8) != cudaSuccess) { gq_decoder_destroy(dec); GQ_FAIL(GQ_E_NOMEM, "gq_decoder_create: out of device memory"); }
+    *out = dec;
+    return GQ_OK;
+}
+
+extern "C" void gq_decoder_destroy(gq_dec *dec) {
+    if (!dec) return;
+    cudaSetDevice(dec->dem->device);
+    if (dec->kind == GQ_DECODER_MATCHING) gq_matching_destroy(dec);
+    else if (dec->kind == GQ_DECODER_BP_MINSUM) gq_bp_destroy(dec);
+    cudaFree(dec->d_dets); cudaFree(dec->d_obs); cudaFree(dec->d_pred); cudaFree(dec->d_count);
+    cudaFree(dec->d_b8);
+    delete dec;
+}
+
+extern "C" int gq_decoder_get_graph_info(const gq_dec *dec, gq_graph_info *info) {
+    if (!dec || !info) GQ_FAIL(GQ_E_INVALID, "gq_decoder_get_graph_info: NULL argument");
+    memset(info, 0, sizeof(*info));
+    info->num_nodes = dec->dem->D;
+    info->num_edges = dec->num_edges;
+    info->num_boundary_edges = dec->num_boundary;
+    info->fast_capacity = dec->fast_cap;
+    info->max_capacity = dec->max_cap;
+    info->max_distance = dec->max_dist;
+    return GQ_OK;
+}
+
+extern "C" int gq_decoder_get_edges(const gq_dec *dec, uint32_t *u, uint32_t *v, uint32_t *weight,
+                                    uint64_t *obs_mask, double *prob) {
+    if (!dec) GQ_FAIL(GQ_E_INVALID, "gq_decoder_get_edges: NULL argument");
+    size_t n = dec->num_edges;
+    if (u) memcpy(u, dec->eu.data(), n * 4);
+    if (v) memcpy(v, dec->ev.data(), n * 4);
+    if (weight) memcpy(weight, dec->ew.data(), n * 4);
+    if (obs_mask) memcpy(obs_mask, dec->eobs.data(), n * 8);
+    if (prob) memcpy(prob, dec->eprob.data(), n * 8);
+    return GQ_OK;
+}
+
+static int decode_dispatch(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
+                           int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out, int *launches) {
+    if (dec->kind == GQ_DECODER_MATCHING)
+        return gq_matching_decode(dec, dets_sm, nshots, pred_sm, weight_out, flags_out, corr_out, launches);
+    return gq_bp_decode(dec, dets_sm, nshots, pred_sm, weight_out, flags_out, corr_out, launches);
+}
+
+extern "C" int gq_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
+                         int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out) {
+    if (!dec || !dets_sm || !pred_sm) GQ_FAIL(GQ_E_INVALID, "gq_decode: NULL argument");
+    if (nshots == 0) return GQ_OK;
+    GQ_CUDA(cudaSetDevice(dec->dem->device));
+    int launches = 0;
+    return decode_dispatch(dec, dets_sm, nshots, pred_sm, weight_out, flags_out, corr_out, &launches);
+}
+
+static int ensure_scratch(gq_dec *dec, uint64_t nshots) {
+    if (dec->scratch_shots >= nshots) return GQ_OK;
+    cudaFree(dec->d_dets); cudaFree(dec->d_obs); cudaFree(dec->d_pred);
+    dec->d_dets = dec->d_obs = dec->d_pred = nullptr;
+    dec->scratch_shots = 0;
+    gq_dem *dem = dec->dem;
+    GQ_CUDA(cudaMalloc((void **)&dec->d_dets, nshots * dem->DW * 4));
+    GQ_CUDA(cudaMalloc((void **)&dec->d_obs, nshots * dem->OW * 4));
+    GQ_CUDA(cudaMalloc((void **)&dec->d_pred, nshots * dem->OW * 4));
+    dec->scratch_shots = nshots;
+    return GQ_OK;
+}
+
+extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots, uint8_t *pred_b8) {
+    if (!dec || !dets_b8 || !pred_b8) GQ_FAIL(GQ_E_INVALID, "gq_decode_b8: NULL argument");
+    if (nshots == 0) return GQ_OK;
+    gq_dem *dem = dec->dem;
+    GQ_CUDA(cudaSetDevice(dem->device));
+    const size_t db = (dem->D + 7) / 8, ob = std::max<size_t>(1, (dem->O + 7) / 8);
+    const uint64_t chunk = 1ull << 20;
+    cudaEvent_t e0, e1, e2, e3;
+    GQ_CUDA(cudaEventCreate(&e0)); GQ_CUDA(cudaEventCreate(&e1));
+    GQ_CUDA(cudaEventCreate(&e2)); GQ_CUDA(cudaEventCreate(&e3));
+    double t_h2d = 0, t_dec = 0, t_d2h = 0;
+    int launches = 0;
+    int rc = ensure_scratch(dec, std::min(chunk, nshots));
+    if (rc) return rc;
+    for (uint64_t s0 = 0; s0 < nshots; s0 += chunk) {
+        uint64_t ns = std::min(chunk, nshots - s0);
+        GQ_CUDA(cudaEventRecord(e0, dem->stream));
+        // b8 rows -> 4-byte aligned rows (same bit order, zero padded)
+        GQ_CUDA(cudaMemsetAsync(dec->d_dets, 0, ns * dem->DW * 4, dem->stream));
+        GQ_CUDA(cudaMemcpy2DAsync(dec->d_dets, (size_t)dem->DW * 4, dets_b8 + s0 * db, db, db, ns,
+                                  cudaMemcpyHostToDevice, dem->stream));
+        GQ_CUDA(cudaEventRecord(e1, dem->stream));
+        rc = decode_dispatch(dec, dec->d_dets, ns, dec->d_pred, nullptr, nullptr, nullptr, &launches);
+        if (rc) return rc;
+        GQ_CUDA(cudaEventRecord(e2, dem->stream));
+        GQ_CUDA(cudaMemcpy2DAsync(pred_b8 + s0 * ob, ob, dec->d_pred, (size_t)dem->OW * 4, ob, ns,
+                                  cudaMemcpyDeviceToHost, dem->stream));
+        GQ_CUDA(cudaEventRecord(e3, dem->stream));
+        GQ_CUDA(cudaStreamSynchronize(dem->stream));
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1); t_h2d += ms;
+        cudaEventElapsedTime(&ms, e1, e2); t_dec += ms;
+        cudaEventElapsedTime(&ms, e2, e3); t_d2h += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    double *t = dec->timing;
+    t[0] = 0; t[1] = t_dec; t[2] = 0; t[3] = t_h2d + t_dec + t_d2h; t[4] = t_h2d; t[5] = t_d2h; t[6] = launches; t[7] = 0;
+    return GQ_OK;
+}
+
+extern "C" int gq_collect(gq_dem *dem, gq_dec *dec, uint64_t seed, uint64_t shot0, uint64_t nshots,
+                          uint64_t max_errors, uint64_t out[3]) {
+    if (!dem || !dec || !out) GQ_FAIL(GQ_E_INVALID, "gq_collect: NULL argument");
+    if (dec->dem != dem) GQ_FAIL(GQ_E_INVALID, "gq_collect: decoder was built for another DEM");
+    if (shot0 % dem->tile_shots) GQ_FAIL(GQ_E_INVALID, "gq_collect: shot0 must be a multiple of tile_shots");
+    out[0] = out[1] = out[2] = 0;
+    if (nshots == 0) return GQ_OK;
+    GQ_CUDA(cudaSetDevice(dem->device));
+    const uint64_t chunk = 1ull << 20;  // multiple of every tile size
+    int rc = ensure_scratch(dec, std::min(chunk, nshots));
+    if (rc) return rc;
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; ++i) GQ_CUDA(cudaEventCreate(&ev[i]));
+    GQ_CUDA(cudaMemsetAsync(dec->d_count, 0, 8, dem->stream));
+    double t_s = 0, t_d = 0, t_c = 0;
+    int launches = 0;
+    uint64_t done = 0, errors = 0;
+    while (done < nshots) {
+        uint64_t ns = std::min(chunk, nshots - done);
+        GQ_CUDA(cudaEventRecord(ev[0], dem->stream));
+        rc = gq_sample(dem, seed, shot0 + done, ns, dec->d_dets, dec->d_obs, nullptr);
+        if (rc) return rc;
+        ++launches;
+        GQ_CUDA(cudaEventRecord(ev[1], dem->stream));
+        rc = decode_dispatch(dec, dec->d_dets, ns, dec->d_pred, nullptr, nullptr, nullptr, &launches);
+        if (rc) return rc;
+        GQ_CUDA(cudaEventRecord(ev[2], dem->stream));
+        rc = gq_count_errors(dem, dec->d_pred, dec->d_obs, ns, dec->d_count);
+        if (rc) return rc;
+        ++launches;
+        GQ_CUDA(cudaEventRecord(ev[3], dem->stream));
+        done += ns;
+        if (max_errors || done >= nshots) {
+            GQ_CUDA(cudaMemcpyAsync(&errors, dec->d_count, 8, cudaMemcpyDeviceToHost, dem->stream));
+        }
+        GQ_CUDA(cudaStreamSynchronize(dem->stream));
+        float ms;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]); t_s += ms;
+        cudaEventElapsedTime(&ms, ev[1], ev[2]); t_d += ms;
+        cudaEventElapsedTime(&ms, ev[2], ev[3]); t_c += ms;
+        if (max_errors && errors >= max_errors) break;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    out[0] = done; out[1] = errors; out[2] = 0;
+    double *t = dec->timing;
+    t[0] = t_s; t[1] = t_d; t[2] = t_c; t[3] = t_s + t_d + t_c; t[4] = 0; t[5] = 8; t[6] = launches; t[7] = 0;
+    return GQ_OK;
+}
+
+extern "C" int gq_last_timing(const gq_dec *dec, double out_ms[8]) {
+    if (!dec || !out_ms) GQ_FAIL(GQ_E_INVALID, "gq_last_timing: NULL argument");
+    memcpy(out_ms, dec->timing, sizeof(double) * 8);
+    return GQ_OK;
+}

@@ -1,0 +1,113 @@
+// Internal declarations shared by the translation units of libgqec_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gqec_b200.h"
+
+void gq_set_error(const std::string &msg);
+
+#define GQ_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            gq_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));              \
+            return GQ_E_CUDA;                                                              \
+        }                                                                                  \
+    } while (0)
+
+#define GQ_FAIL(code, msg)      \
+    do {                        \
+        gq_set_error(msg);      \
+        return (code);          \
+    } while (0)
+
+// one probability class of the sampler (all mechanisms with the same p)
+struct GqClass {
+    float inv_log1m;      // 1 / log(1 - p)   (negative; -0 for p == 1)
+    uint32_t mech_start;  // first mechanism (class-sorted order)
+    uint32_t mech_count;
+    uint32_t seg_len;     // flat (mechanism, shot) indices per RNG segment
+    uint32_t seg_first;   // index of the class's first segment
+    uint32_t flat_size;   // mech_count * tile_shots
+};
+
+struct gq_dem {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t D = 0, O = 0, M = 0;
+    uint32_t DW = 0, OW = 0;
+    uint32_t tile_shots = 0, tile_log2 = 0;
+    uint32_t nclasses = 0, nsegments = 0;
+    double sum_p = 0;
+    int num_sms = 148;
+    // host copies (original order)
+    std::vector<double> p;
+    std::vector<uint32_t> det_indptr, det_idx, obs_indptr, obs_idx;
+    std::vector<uint32_t> comp_indptr, comp_a, comp_b;
+    std::vector<uint64_t> comp_obs;
+    bool has_components = false;
+    // device: class-sorted mechanisms for the sampler
+    GqClass *d_classes = nullptr;
+    uint32_t *d_seg_first = nullptr;   // [nclasses + 1]
+    uint32_t *d_mech_ptr = nullptr;    // [M + 1]
+    uint32_t *d_mech_det = nullptr;    // [nnz]
+    uint32_t *d_mech_obs = nullptr;    // [M] observable mask
+    uint32_t *d_mech_orig = nullptr;   // [M] original mechanism index
+    // device: transposed CSR (row = detector, then observables) for the bit-sliced extractor
+    uint32_t *d_row_ptr = nullptr;     // [D + O + 1]
+    uint32_t *d_row_mech = nullptr;    // [nnz_H + nnz_L]
+};
+
+struct gq_dec {
+    gq_dem *dem = nullptr;
+    int kind = 0;
+    gq_decoder_params params{};
+    double timing[8] = {0};
+    // ---- matching
+    uint32_t num_edges = 0, num_boundary = 0;
+    std::vector<uint32_t> eu, ev, ew;
+    std::vector<uint64_t> eobs;
+    std::vector<double> eprob;
+    uint32_t fast_cap = 0, max_cap = 0, max_dist = 0;
+    uint16_t *d_dist = nullptr;        // [D][D+1]
+    uint8_t *d_pobs = nullptr;         // [D][D+1] observable mask of the shortest path
+    uint16_t *d_next = nullptr;        // [D][D+1] next node on the shortest path (0xFFFF = boundary hop)
+    uint32_t *d_adj_ptr = nullptr;     // [D+1]   adjacency for corrections
+    uint32_t *d_adj_node = nullptr;    // neighbour (D = boundary)
+    uint32_t *d_adj_edge = nullptr;    // edge id
+    void *d_ws_fast = nullptr;         // per-warp workspaces
+    void *d_ws_big = nullptr;
+    size_t ws_fast_bytes = 0, ws_big_bytes = 0;
+    int nwarps_fast = 0, nwarps_big = 0;
+    uint32_t *d_overflow = nullptr;    // [1 + capacity] overflow shot list
+    uint32_t overflow_cap = 0;
+    // ---- BP
+    uint32_t *d_chk_ptr = nullptr, *d_chk_var = nullptr, *d_var_ptr = nullptr, *d_var_edge = nullptr;
+    float *d_prior = nullptr;
+    uint32_t *d_var_obs = nullptr;
+    float *d_bp_msgs = nullptr;
+    size_t bp_msgs_per_block = 0;
+    int bp_blocks = 0;
+    uint32_t bp_nnz = 0;
+    // ---- scratch for gq_collect / gq_decode_b8
+    uint32_t *d_dets = nullptr, *d_obs = nullptr, *d_pred = nullptr;
+    uint64_t scratch_shots = 0;
+    uint64_t *d_count = nullptr;
+    uint8_t *d_b8 = nullptr;
+    uint64_t b8_bytes = 0;
+};
+
+// matching.cu
+int gq_matching_create(gq_dec *dec);
+void gq_matching_destroy(gq_dec *dec);
+int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
+                       int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out, int *launches);
+// bp.cu
+int gq_bp_create(gq_dec *dec);
+void gq_bp_destroy(gq_dec *dec);
+int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
+                 int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out, int *launches);

@@ -1,0 +1,407 @@
+// K3a: batched exact matching decoder, one shot per warp.
+//
+// Set-up (host, once per DEM): graphlike pieces of the DEM are merged into the matching graph with
+// PyMatching's conventions (parallel edges merge with p1(1-p2)+p2(1-p1), weight
+// ln((1-p)/p), discretised to integers), then all-pairs shortest paths (one Dijkstra per node, one
+// more from the boundary) give three (D+1)x(D+1) tables resident in HBM/L2: distance (u16),
+// observable mask of that path (u8), and the path's next hop (u16, only if corrections are wanted).
+//
+// Kernel: a warp extracts the defects of its shot from the bit-packed syndrome (ballot/popc
+// compaction), gathers the dense weight matrix W[i][j] = min(d(i,j), b(i)+b(j)) of those defects
+// from the distance table, runs the warp-cooperative blossom solver (blossom_warp.cuh) and XORs the
+// path observables of the matched pairs into the prediction.  Shots with more defects than the
+// fast tier's capacity are queued and solved by a second launch with a larger workspace.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <queue>
+#include <thread>
+
+#include "blossom_warp.cuh"
+#include "gq_common.h"
+
+struct MatchArgs {
+    const uint32_t *dets;
+    uint32_t *pred;
+    int32_t *weight_out;
+    uint8_t *flags_out;
+    uint32_t *corr_out;
+    const uint32_t *list;     // optional shot list (overflow pass)
+    uint64_t nitems;
+    uint32_t D, DW, OW, EW;
+    uint32_t cap;             // even; real defects handled: cap - 1
+    const uint16_t *dist;
+    const uint8_t *pobs;
+    const uint16_t *next;
+    const uint32_t *adj_ptr, *adj_node, *adj_edge;
+    char *ws;
+    size_t ws_stride;
+    uint32_t *overflow;       // [0] count, [1] max defects, [2..] shots
+    uint32_t overflow_cap;
+};
+
+__device__ __forceinline__ void walk_path(const MatchArgs &a, uint32_t cur, uint32_t target, uint32_t *corr_row) {
+    const uint32_t N = a.D + 1;
+    for (uint32_t guard = 0; guard <= a.D && cur != target; ++guard) {
+        uint32_t nx = a.next[(size_t)target * N + cur];
+        if (nx == 0xFFFFu) nx = a.D;  // hop onto the boundary
+        uint32_t e = 0xFFFFFFFFu;
+        for (uint32_t q = a.adj_ptr[cur]; q < a.adj_ptr[cur + 1]; ++q)
+            if (a.adj_node[q] == nx) { e = a.adj_edge[q]; break; }
+        if (e == 0xFFFFFFFFu) return;
+        atomicXor(&corr_row[e >> 5], 1u << (e & 31));
+        cur = nx;
+    }
+}
+
+__global__ void __launch_bounds__(256) match_kernel(MatchArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t N = a.D + 1;
+    const int cap = (int)a.cap;
+    char *mem = a.ws + warp * a.ws_stride;
+    gqb::Solver S;
+    gqb::ws_bind(S.w, mem, cap);
+    S.cap = cap; S.nb = cap / 2;
+    uint16_t *def = (uint16_t *)(mem + gqb::ws_bytes(cap));
+    uint16_t *bd = def + cap;
+    const uint16_t *brow = a.dist + (size_t)a.D * N;   // distances to the boundary
+    const uint8_t *bobs = a.pobs + (size_t)a.D * N;
+
+    for (uint64_t item = warp; item < a.nitems; item += nwarps) {
+        const uint64_t shot = a.list ? a.list[item] : item;
+        const uint32_t *row = a.dets + shot * a.DW;
+        // ---- defect list (ascending detector index)
+        int n0 = 0;
+        for (uint32_t w0 = 0; w0 < a.DW; w0 += 32) {
+            uint32_t wi = w0 + lane;
+            uint32_t word = wi < a.DW ? row[wi] : 0u;
+            if (wi == a.DW - 1 && (a.D & 31)) word &= (1u << (a.D & 31)) - 1;
+            int cnt = __popc(word);
+            int pre = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += t;
+            }
+            int tot = __shfl_sync(0xffffffffu, pre, 31);
+            int pos = n0 + pre - cnt;
+            while (word) {
+                int b = __ffs(word) - 1;
+                word &= word - 1;
+                if (pos < cap) def[pos] = (uint16_t)(wi * 32 + b);
+                ++pos;
+            }
+            n0 += tot;
+        }
+        __syncwarp();
+        if (n0 > cap - 1) {
+            if (lane == 0 && a.overflow) {
+                uint32_t idx = atomicAdd(&a.overflow[0], 1u);
+                atomicMax(&a.overflow[1], (uint32_t)n0);
+                if (idx < a.overflow_cap) a.overflow[2 + idx] = (uint32_t)shot;
+            }
+            if (lane == 0 && !a.overflow && a.flags_out) a.flags_out[shot] = 2;
+            continue;
+        }
+        uint32_t pm = 0;
+        int wt = 0;
+        int rc = 0;
+        if (n0 > 0) {
+            const int n = n0 + (n0 & 1);
+            for (int i = lane; i < n0; i += 32) bd[i] = brow[def[i]];
+            __syncwarp();
+            for (int i = 0; i < n0; ++i) {
+                const uint32_t di = def[i];
+                const uint32_t bi = bd[i];
+                const uint16_t *drow = a.dist + (size_t)di * N;
+                uint16_t *wrow = S.w.W + i * S.w.wstride;
+                for (int j = lane; j < n0; j += 32) {
+                    uint32_t d = drow[def[j]];
+                    uint32_t bj = bd[j];
+                    uint32_t s = (bi == 0xFFFFu || bj == 0xFFFFu) ? 0xFFFFu : min(bi + bj, 0xFFFEu);
+                    wrow[j] = (uint16_t)min(d, s);
+                }
+                if (n != n0 && lane == 0) {
+                    wrow[n0] = (uint16_t)bi;
+                    S.w.W[n0 * S.w.wstride + i] = (uint16_t)bi;
+                }
+            }
+            if (n != n0 && lane == 0) S.w.W[n0 * S.w.wstride + n0] = 0xFFFFu;
+            __syncwarp();
+            S.n = n;
+            rc = S.solve();
+            __syncwarp();
+            if (rc == 0) {
+                uint32_t *corr_row = a.corr_out ? a.corr_out + shot * a.EW : nullptr;
+                for (int i = lane; i < n0; i += 32) {
+                    int j = S.w.mate[i];
+                    const uint32_t di = def[i];
+                    if (j == n0) {  // paired with the virtual boundary vertex
+                        pm ^= bobs[di];
+                        wt += bd[i];
+                        if (corr_row) walk_path(a, di, a.D, corr_row);
+                    } else if (j > i) {
+                        const uint32_t dj = def[j];
+                        uint32_t d = a.dist[(size_t)dj * N + di];
+                        uint32_t s = (bd[i] == 0xFFFFu || bd[j] == 0xFFFFu) ? 0xFFFFu : (uint32_t)bd[i] + bd[j];
+                        if (d <= s) {
+                            pm ^= a.pobs[(size_t)dj * N + di];
+                            wt += (int)d;
+                            if (corr_row) walk_path(a, di, dj, corr_row);
+                        } else {
+                            pm ^= bobs[di] ^ bobs[dj];
+                            wt += (int)s;
+                            if (corr_row) { walk_path(a, di, a.D, corr_row); walk_path(a, dj, a.D, corr_row); }
+                        }
+                    }
+                }
+                pm = __reduce_xor_sync(0xffffffffu, pm);
+                wt = __reduce_add_sync(0xffffffffu, wt);
+            }
+        }
+        if (lane == 0) {
+            a.pred[shot * a.OW] = rc == 0 ? pm : 0u;
+            for (uint32_t w = 1; w < a.OW; ++w) a.pred[shot * a.OW + w] = 0u;
+            if (a.weight_out) a.weight_out[shot] = rc == 0 ? wt : -1;
+            if (a.flags_out) a.flags_out[shot] = (uint8_t)(rc == 0 ? 0 : (rc == 1 ? 1 : 2));
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: graph + tables
+// ------------------------------------------------------------------------------------------------
+static size_t warp_ws_bytes(int cap) { return (gqb::ws_bytes(cap) + (size_t)cap * 4 + 15) & ~(size_t)15; }
+static int even_up(int x) { return (x + 1) & ~1; }
+
+int gq_matching_create(gq_dec *dec) {
+    gq_dem *dem = dec->dem;
+    const uint32_t D = dem->D, N = D + 1;
+    if (dem->O > 8) GQ_FAIL(GQ_E_UNSUPPORTED, "matching decoder: more than 8 observables are not supported");
+    if (D >= 0xFFFEu) GQ_FAIL(GQ_E_UNSUPPORTED, "matching decoder: too many detectors");
+    if (D == 0) GQ_FAIL(GQ_E_INVALID, "matching decoder: the DEM has no detectors");
+    // ---- graphlike pieces -> merged edges
+    std::map<std::pair<uint32_t, uint32_t>, std::pair<double, uint64_t>> table;
+    auto add_piece = [&](uint32_t a, uint32_t b, uint64_t om, double p) {
+        if (a == GQ_NO_DET) return;
+        if (b != GQ_NO_DET && b < a) std::swap(a, b);
+        if (b != GQ_NO_DET && a == b) return;
+        auto key = std::make_pair(a, b);
+        auto it = table.find(key);
+        if (it == table.end()) table[key] = std::make_pair(p, om);
+        else it->second.first = it->second.first * (1 - p) + p * (1 - it->second.first);
+    };
+    for (uint32_t m = 0; m < dem->M; ++m) {
+        if (dem->has_components) {
+            for (uint32_t c = dem->comp_indptr[m]; c < dem->comp_indptr[m + 1]; ++c)
+                add_piece(dem->comp_a[c], dem->comp_b[c], dem->comp_obs[c], dem->p[m]);
+        } else {
+            uint32_t b = dem->det_indptr[m], e = dem->det_indptr[m + 1];
+            if (e - b < 1 || e - b > 2) continue;  // PyMatching ignores non-graphlike mechanisms
+            uint64_t om = 0;
+            for (uint32_t q = dem->obs_indptr[m]; q < dem->obs_indptr[m + 1]; ++q) om ^= 1ull << dem->obs_idx[q];
+            add_piece(dem->det_idx[b], e - b == 2 ? dem->det_idx[b + 1] : GQ_NO_DET, om, dem->p[m]);
+        }
+    }
+    int levels = dec->params.weight_levels > 0 ? dec->params.weight_levels : 1000;
+    double wmax = 0;
+    std::vector<double> wf;
+    for (auto &kv : table) {
+        double p = std::min(std::max(kv.second.first, 1e-300), 0.5);
+        double w = log((1 - p) / p);
+        wf.push_back(w);
+        wmax = std::max(wmax, w);
+        dec->eu.push_back(kv.first.first);
+        dec->ev.push_back(kv.first.second);
+        dec->eobs.push_back(kv.second.second);
+        dec->eprob.push_back(kv.second.first);
+        if (kv.first.second == GQ_NO_DET) dec->num_boundary++;
+    }
+    dec->num_edges = (uint32_t)dec->eu.size();
+    for (double w : wf) {
+        double v = wmax > 0 ? rint(w * (levels / wmax)) : 1.0;
+        dec->ew.push_back((uint32_t)std::max(1.0, v));
+    }
+    // ---- adjacency (node D = boundary)
+    std::vector<uint32_t> adj_ptr(N + 1, 0);
+    for (uint32_t e = 0; e < dec->num_edges; ++e) {
+        uint32_t a = dec->eu[e], b = dec->ev[e] == GQ_NO_DET ? D : dec->ev[e];
+        adj_ptr[a + 1]++; adj_ptr[b + 1]++;
+    }
+    for (uint32_t i = 0; i < N; ++i) adj_ptr[i + 1] += adj_ptr[i];
+    std::vector<uint32_t> adj_node(adj_ptr[N]), adj_edge(adj_ptr[N]);
+    {
+        std::vector<uint32_t> fill(adj_ptr.begin(), adj_ptr.end() - 1);
+        for (uint32_t e = 0; e < dec->num_edges; ++e) {
+            uint32_t a = dec->eu[e], b = dec->ev[e] == GQ_NO_DET ? D : dec->ev[e];
+            adj_node[fill[a]] = b; adj_edge[fill[a]++] = e;
+            adj_node[fill[b]] = a; adj_edge[fill[b]++] = e;
+        }
+    }
+    // ---- all-pairs shortest paths: row s = Dijkstra tree rooted at s (row D: rooted at the boundary)
+    const bool want_next = dec->params.with_corrections != 0;
+    std::vector<uint16_t> dist((size_t)N * N, 0xFFFFu), nexttab;
+    std::vector<uint8_t> pobs((size_t)N * N, 0);
+    if (want_next) nexttab.assign((size_t)N * N, 0xFFFFu);
+    std::vector<uint32_t> row_max(N, 0);
+    std::atomic<bool> too_far(false);
+    auto worker = [&](uint32_t s_begin, uint32_t s_end) {
+        std::vector<uint64_t> d(N);
+        std::vector<uint8_t> po(N);
+        std::vector<uint32_t> pr(N);
+        std::vector<char> done(N);
+        typedef std::pair<uint64_t, uint32_t> QI;
+        for (uint32_t s = s_begin; s < s_end; ++s) {
+            std::fill(d.begin(), d.end(), ~0ull);
+            std::fill(po.begin(), po.end(), 0);
+            std::fill(pr.begin(), pr.end(), 0xFFFFFFFFu);
+            std::fill(done.begin(), done.end(), 0);
+            std::priority_queue<QI, std::vector<QI>, std::greater<QI>> pq;
+            d[s] = 0;
+            pq.push(QI(0, s));
+            while (!pq.empty()) {
+                QI it = pq.top(); pq.pop();
+                uint32_t u = it.second;
+                if (done[u]) continue;
+                done[u] = 1;
+                if (u == D && s != D) continue;  // the boundary is a sink, never a through-node
+                for (uint32_t q = adj_ptr[u]; q < adj_ptr[u + 1]; ++q) {
+                    uint32_t v = adj_node[q], e = adj_edge[q];
+                    if (v == D && s == D) continue;
+                    uint64_t nd = it.first + dec->ew[e];
+                    if (nd < d[v]) {
+                        d[v] = nd; po[v] = po[u] ^ (uint8_t)dec->eobs[e]; pr[v] = u;
+                        pq.push(QI(nd, v));
+                    }
+                }
+            }
+            uint32_t mx = 0;
+            for (uint32_t t = 0; t < N; ++t) {
+                if (d[t] == ~0ull) continue;
+                if (d[t] >= 0xFFFEull) { too_far = true; continue; }
+                dist[(size_t)s * N + t] = (uint16_t)d[t];
+                pobs[(size_t)s * N + t] = po[t];
+                if (want_next && t != s) nexttab[(size_t)s * N + t] = pr[t] == D ? 0xFFFFu : (uint16_t)pr[t];
+                mx = std::max<uint32_t>(mx, (uint32_t)d[t]);
+            }
+            row_max[s] = mx;
+        }
+    };
+    {
+        unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+        nt = std::min<unsigned>(nt, N);
+        std::vector<std::thread> th;
+        uint32_t per = (N + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; ++t) {
+            uint32_t b = std::min<uint32_t>(N, t * per), e = std::min<uint32_t>(N, b + per);
+            if (b < e) th.emplace_back(worker, b, e);
+        }
+        for (auto &t : th) t.join();
+    }
+    if (too_far) GQ_FAIL(GQ_E_UNSUPPORTED, "matching decoder: path lengths exceed 16 bits; lower weight_levels");
+    dec->max_dist = *std::max_element(row_max.begin(), row_max.end());
+    // ---- capacities: expected defect count from the DEM
+    std::vector<double> keep(D, 1.0);
+    for (uint32_t m = 0; m < dem->M; ++m)
+        for (uint32_t q = dem->det_indptr[m]; q < dem->det_indptr[m + 1]; ++q) keep[dem->det_idx[q]] *= 1 - 2 * dem->p[m];
+    double mu = 0;
+    for (uint32_t d = 0; d < D; ++d) mu += 0.5 * (1 - keep[d]);
+    int fast = dec->params.fast_capacity > 0 ? dec->params.fast_capacity : (int)(mu + 6 * sqrt(2 * mu + 1) + 8);
+    fast = std::min<int>(even_up(fast + 1), even_up((int)D + 1));
+    fast = std::max(fast, 4);
+    dec->fast_cap = (uint32_t)fast;
+    dec->max_cap = (uint32_t)even_up((int)D + 1);
+    // ---- upload
+    GQ_CUDA(cudaMalloc((void **)&dec->d_dist, dist.size() * 2));
+    GQ_CUDA(cudaMemcpy(dec->d_dist, dist.data(), dist.size() * 2, cudaMemcpyHostToDevice));
+    GQ_CUDA(cudaMalloc((void **)&dec->d_pobs, pobs.size()));
+    GQ_CUDA(cudaMemcpy(dec->d_pobs, pobs.data(), pobs.size(), cudaMemcpyHostToDevice));
+    if (want_next) {
+        GQ_CUDA(cudaMalloc((void **)&dec->d_next, nexttab.size() * 2));
+        GQ_CUDA(cudaMemcpy(dec->d_next, nexttab.data(), nexttab.size() * 2, cudaMemcpyHostToDevice));
+        GQ_CUDA(cudaMalloc((void **)&dec->d_adj_ptr, adj_ptr.size() * 4));
+        GQ_CUDA(cudaMemcpy(dec->d_adj_ptr, adj_ptr.data(), adj_ptr.size() * 4, cudaMemcpyHostToDevice));
+        GQ_CUDA(cudaMalloc((void **)&dec->d_adj_node, std::max<size_t>(adj_node.size(), 1) * 4));
+        GQ_CUDA(cudaMemcpy(dec->d_adj_node, adj_node.data(), adj_node.size() * 4, cudaMemcpyHostToDevice));
+        GQ_CUDA(cudaMalloc((void **)&dec->d_adj_edge, std::max<size_t>(adj_edge.size(), 1) * 4));
+        GQ_CUDA(cudaMemcpy(dec->d_adj_edge, adj_edge.data(), adj_edge.size() * 4, cudaMemcpyHostToDevice));
+    }
+    // ---- fast-tier workspaces: 2 blocks of 8 warps per SM
+    dec->nwarps_fast = dem->num_sms * 2 * 8;
+    dec->ws_fast_bytes = warp_ws_bytes(fast);
+    GQ_CUDA(cudaMalloc(&dec->d_ws_fast, dec->ws_fast_bytes * dec->nwarps_fast));
+    dec->overflow_cap = 1u << 20;
+    GQ_CUDA(cudaMalloc((void **)&dec->d_overflow, (2 + (size_t)dec->overflow_cap) * 4));
+    return GQ_OK;
+}
+
+void gq_matching_destroy(gq_dec *dec) {
+    cudaFree(dec->d_dist); cudaFree(dec->d_pobs); cudaFree(dec->d_next);
+    cudaFree(dec->d_adj_ptr); cudaFree(dec->d_adj_node); cudaFree(dec->d_adj_edge);
+    cudaFree(dec->d_ws_fast); cudaFree(dec->d_ws_big); cudaFree(dec->d_overflow);
+}
+
+int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
+                       int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out, int *launches) {
+    gq_dem *dem = dec->dem;
+    if (corr_out && !dec->d_next) GQ_FAIL(GQ_E_INVALID, "gq_decode: corrections need with_corrections=1 at creation");
+    MatchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dets = dets_sm; a.pred = pred_sm; a.weight_out = weight_out; a.flags_out = flags_out;
+    a.corr_out = corr_out;
+    a.D = dem->D; a.DW = dem->DW; a.OW = dem->OW; a.EW = (dec->num_edges + 31) / 32;
+    a.dist = dec->d_dist; a.pobs = dec->d_pobs; a.next = dec->d_next;
+    a.adj_ptr = dec->d_adj_ptr; a.adj_node = dec->d_adj_node; a.adj_edge = dec->d_adj_edge;
+    // the overflow list is bounded: process in slices so it can never overrun
+    const uint64_t slice = 1ull << 22;
+    for (uint64_t s0 = 0; s0 < nshots; s0 += slice) {
+        uint64_t ns = std::min(slice, nshots - s0);
+        GQ_CUDA(cudaMemsetAsync(dec->d_overflow, 0, 8, dem->stream));
+        MatchArgs b = a;
+        b.dets = dets_sm + s0 * dem->DW;
+        b.pred = pred_sm + s0 * dem->OW;
+        if (weight_out) b.weight_out = weight_out + s0;
+        if (flags_out) b.flags_out = flags_out + s0;
+        if (corr_out) b.corr_out = corr_out + s0 * a.EW;
+        b.list = nullptr; b.nitems = ns;
+        b.cap = dec->fast_cap;
+        b.ws = (char *)dec->d_ws_fast; b.ws_stride = dec->ws_fast_bytes;
+        b.overflow = dec->d_overflow; b.overflow_cap = dec->overflow_cap;
+        int blocks = (int)std::min<uint64_t>((ns + 7) / 8, (uint64_t)dec->nwarps_fast / 8);
+        match_kernel<<<blocks, 256, 0, dem->stream>>>(b);
+        GQ_CUDA(cudaGetLastError());
+        ++*launches;
+        uint32_t ovf[2];
+        GQ_CUDA(cudaMemcpyAsync(ovf, dec->d_overflow, 8, cudaMemcpyDeviceToHost, dem->stream));
+        GQ_CUDA(cudaStreamSynchronize(dem->stream));
+        if (ovf[0] == 0) continue;
+        if (ovf[0] > dec->overflow_cap) GQ_FAIL(GQ_E_INTERNAL, "matching decoder: overflow list overrun; raise fast_capacity");
+        int cap = std::min<int>(even_up((int)ovf[1] + 1), (int)dec->max_cap);
+        size_t wsb = warp_ws_bytes(cap);
+        int nw = (int)std::min<uint64_t>(ovf[0], (uint64_t)dem->num_sms * 8);
+        size_t budget = (size_t)8 << 30;
+        nw = (int)std::max<size_t>(1, std::min<size_t>(nw, budget / wsb));
+        nw = std::max(8, (nw / 8) * 8);
+        if (wsb * nw > dec->ws_big_bytes) {
+            cudaFree(dec->d_ws_big);
+            dec->d_ws_big = nullptr; dec->ws_big_bytes = 0;
+            GQ_CUDA(cudaMalloc(&dec->d_ws_big, wsb * nw));
+            dec->ws_big_bytes = wsb * nw;
+        }
+        MatchArgs c = b;
+        c.list = dec->d_overflow + 2; c.nitems = ovf[0];
+        c.cap = (uint32_t)cap;
+        c.ws = (char *)dec->d_ws_big; c.ws_stride = wsb;
+        c.overflow = nullptr; c.overflow_cap = 0;
+        match_kernel<<<nw / 8, 256, 0, dem->stream>>>(c);
+        GQ_CUDA(cudaGetLastError());
+        ++*launches;
+    }
+    return GQ_OK;
+}
