@@ -257,6 +257,12 @@ class DecoderHandle:
         n = dets_sm.shape[0]
         dev = dets_sm.device
         pred = torch.zeros((n, self.demh.OW), dtype=torch.int32, device=dev)
+        if n == 0:
+            want = [want_weights, want_flags, want_corrections]
+            extra = [torch.zeros(0, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.uint8, device=dev),
+                     torch.zeros((0, 1), dtype=torch.int32, device=dev)]
+            out = [pred] + [e for e, w in zip(extra, want) if w]
+            return out[0] if len(out) == 1 else tuple(out)
         wts = torch.zeros(n, dtype=torch.int32, device=dev) if want_weights else None
         flags = torch.zeros(n, dtype=torch.uint8, device=dev) if want_flags else None
         corr = None

@@ -10,7 +10,7 @@ static void default_params(gq_decoder_params *p) {
     memset(p, 0, sizeof(*p));
     p->weight_levels = 1000;
     p->bp_max_iter = 30;
-    p->bp_alpha = 0.625f;
+    p->bp_alpha = 0.9f;
 }
 
 extern "C" int gq_decoder_create(gq_dem *dem, int kind, const gq_decoder_params *params, gq_dec **out) {

@@ -48,7 +48,7 @@ typedef struct gq_decoder_params {
     int32_t fast_capacity;     /* matching: defects handled by the fast tier; 0 = choose from the DEM */
     int32_t with_corrections;  /* matching: keep the next-hop table so corrections can be emitted */
     int32_t bp_max_iter;       /* BP: iteration cap (default 30) */
-    float bp_alpha;            /* BP: min-sum normalisation factor (default 0.625) */
+    float bp_alpha;            /* BP: min-sum normalisation factor (default 0.9) */
     int32_t reserved[8];
 } gq_decoder_params;
 

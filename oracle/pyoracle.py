@@ -219,7 +219,7 @@ def collect(dem, seed: int, nshots: int, nthreads: int = 1, oracle: MwpmOracle |
 # ------------------------------------------------------------------------------------------
 
 class BpOracle:
-    def __init__(self, dem, max_iter: int = 30, alpha: float = 0.625):
+    def __init__(self, dem, max_iter: int = 30, alpha: float = 0.9):
         self.dem = dem
         D, M = dem.num_detectors, dem.num_errors
         rows = dem.det_idx.astype(np.int64)

@@ -1,0 +1,50 @@
+"""End-to-end through the reference-facing API: ThresholdLAB.collect_stats on the GPU."""
+import numpy as np
+import pytest
+
+from graphqec_b200 import RepetitionCode, RotatedSurfaceCode, ThresholdLAB, wilson_interval
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_repetition_sweep():
+    """README.md:75-91 of the reference: repetition code threshold sweep (BASELINE configs[0])."""
+    th = ThresholdLAB(configurations=[{"distance": d} for d in [3, 5, 7, 11]], code=RepetitionCode,
+                      error_rates=np.linspace(0, 0.2, 10), decoder="pymatching")
+    assert th.collect_stats(num_workers=4, max_shots=10**5, max_errors=1000, logic_check="Z") is None
+    s = th.samples
+    assert len(s) == 40
+    assert s[0].json_metadata == {"name": "Repetition [[5,1,3]]", "error": 0.0, "n": 5, "k": 1, "d": 3, "r": 3}
+    for st in s:
+        if st.json_metadata["error"] == 0:
+            assert (st.shots, st.errors) == (10**5, 0)     # p = 0 runs to max_shots with no failure
+        else:
+            assert st.shots == 10**5 or st.errors >= 1000
+            assert st.discards == 0 and st.seconds > 0
+    # below threshold (p ~ 0.022) larger distance is better; far above (p = 0.2) it is not
+    ler = {(st.json_metadata["d"], round(st.json_metadata["error"], 3)): st.errors / st.shots for st in s}
+    assert ler[(11, 0.022)] < ler[(3, 0.022)]
+    assert ler[(11, 0.2)] > 0.3
+    curves = th.error_rate_curves()
+    assert len(curves) == 4
+
+
+def test_rotated_point_inside_oracle_interval():
+    th = ThresholdLAB(configurations=[{"distance": 5}], code=RotatedSurfaceCode, error_rates=[0.008])
+    th.collect_stats(max_shots=200_000, max_errors=10**9)
+    st = th.samples[0]
+    assert st.shots == 200_000
+    code = RotatedSurfaceCode(distance=5, depolarize1_rate=0.008, depolarize2_rate=0.008)
+    code.build_memory_circuit(number_of_rounds=5)
+    dem = code.memory_circuit.detector_error_model(decompose_errors=True)
+    n, e = po.collect(dem, seed=5, nshots=100_000, nthreads=8)
+    lo, hi = po.wilson(e, n)
+    glo, ghi = wilson_interval(st.errors, st.shots)
+    assert glo <= hi and lo <= ghi
+
+
+def test_unsupported_decoder_raises():
+    th = ThresholdLAB(configurations=[{"distance": 3}], code=RepetitionCode, error_rates=[0.1], decoder="mwpf")
+    with pytest.raises(NotImplementedError):
+        th.collect_stats(max_shots=100)

@@ -1,0 +1,115 @@
+"""Host logic of ThresholdLAB: task generation, stop rule, rank sharding (gloo, world size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from graphqec_b200 import RepetitionCode, RotatedSurfaceCode, ThresholdLAB, wilson_interval
+from graphqec_b200.lab.threshold import threshold_lab as tl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_init_roundtrip():
+    # reference tests/lab/threshold/test_threshold_lab.py:30-34 (minus the stale attribute)
+    th = ThresholdLAB(configurations=[{"distance": d} for d in [3, 5]], code=RepetitionCode,
+                      error_rates=np.linspace(0, 0.1, 10))
+    assert th.configurations == [{"distance": d} for d in [3, 5]]
+    assert th.code == RepetitionCode
+    assert (th.error_rates == np.linspace(0, 0.1, 10)).all()
+    assert th.decoder == "pymatching"
+    assert th.logic_check() == "Z"       # a method in the reference
+
+
+def test_unknown_decoder_is_not_rejected_at_construction():
+    th = ThresholdLAB(configurations=[], code=RepetitionCode, error_rates=[], decoder="nope")
+    with pytest.raises(AttributeError):
+        th.decoder
+
+
+def test_tasks_metadata_and_rounds():
+    th = ThresholdLAB(configurations=[{"distance": 3}, {"distance": 5}], code=RotatedSurfaceCode,
+                      error_rates=[0.001, 0.002])
+    tasks = list(th.generate_sinter_tasks())
+    assert len(tasks) == 4
+    md = tasks[2].json_metadata
+    assert md == {"name": "Rotated Surface [[49,1,5]]", "error": 0.001, "n": 49, "k": 1, "d": 5, "r": 5}
+    assert tasks[2].circuit.num_detectors == 2 * 12 + 4 * 24
+    with pytest.raises(ValueError):
+        list(ThresholdLAB(configurations=[{"distance": 3}], code=RepetitionCode, error_rates=[0.1]).generate_sinter_tasks(logic_check="X"))
+
+
+def test_check_is_family_sense():
+    class S:  # minimal stand-in for TaskStats
+        def __init__(self, n): self.json_metadata = {"name": n}
+    assert ThresholdLAB.check_is_family([S("a"), S("a")]) is False
+    assert ThresholdLAB.check_is_family([S("a"), S("b")]) is True
+
+
+def test_split_batch_covers_range_exactly():
+    for world in (1, 2, 3, 8):
+        for n in (1, 255, 256, 257, 1000, 16384, 100000):
+            parts = [tl._split_batch(512, n, 256, r, world) for r in range(world)]
+            assert sum(p[1] for p in parts) == n
+            pos = 512
+            for s0, cnt in parts:
+                if cnt:
+                    assert s0 == pos and s0 % 256 == 0
+                    pos += cnt
+
+
+class _FakeDecoder:
+    """Counts one 'error' per shot whose global index is divisible by 1000."""
+
+    def collect(self, seed, shot0, nshots, max_errors):
+        first = -(-shot0 // 1000) * 1000
+        errs = len(range(first, shot0 + nshots, 1000))
+        return nshots, errs, 0
+
+
+def test_stop_rule_single_process():
+    shots, errors, _ = tl._run_task(_FakeDecoder(), 256, 1, 100000, 0, 0, None, 0, 1, 0)
+    assert (shots, errors) == (100000, 100)
+    shots, errors, _ = tl._run_task(_FakeDecoder(), 256, 1, 10**9, 50, 0, None, 0, 1, 0)
+    assert errors >= 50 and shots < 10**6    # stopped early, overshoot allowed like sinter
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from graphqec_b200.lab.threshold import threshold_lab as tl2
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    d, r, w = tl2._dist_info()
+    out = tl2._run_task(_FakeDecoder(), 256, 1, 300000, 0, 0, d, r, w, 0)
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_rank_sharding_gloo_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs: p.join(timeout=60)
+    # both ranks agree, and the totals equal the single-process run: independent of world size
+    assert res[0] == res[1] == (300000, 300, 0)
+
+
+def test_wilson_interval():
+    lo, hi = wilson_interval(10, 1000)
+    assert 0.0048 < lo < 0.0055 and 0.0182 < hi < 0.0185
+    assert wilson_interval(0, 0) == (0.0, 1.0)
+
+
+def test_curves_without_matplotlib():
+    from graphqec_b200.stats import TaskStats
+    th = ThresholdLAB(configurations=[{"distance": 3}], code=RepetitionCode, error_rates=[0.1])
+    th._samples = [TaskStats("x", "pymatching", {"name": "A", "error": 0.1, "r": 3, "k": 1}, shots=1000, errors=100)]
+    (name, xs, ys, lo, hi), = th.error_rate_curves("per_round")
+    assert name == "A" and xs == [0.1]
+    assert abs(ys[0] - (0.5 - 0.5 * (1 - 0.2) ** (1 / 3))) < 1e-12 and lo[0] < ys[0] < hi[0]
