@@ -1,0 +1,464 @@
+// Register-resident variant of the warp-cooperative blossom solver (fast tier, n <= 32*K).
+//
+// Same algorithm and invariants as blossom_warp.cuh (see there), different data placement:
+//  * vertex v lives in slot (v >> 5) of lane (v & 31): its dual, best slack, slack source, top-level
+//    node and that node's label are REGISTERS, so the O(n) sweeps (slack scan of a new outer vertex,
+//    minimum-slack search, dual update) are a few ALU ops per slot plus one shuffle reduction;
+//  * the blossom forest (mate, top, base, parent/sibling links, tree edges), which lane 0 walks
+//    when it augments / shrinks / expands, lives in shared memory;
+//  * the dense weight matrix W stays in an L2-resident scratch, read one coalesced row per scan.
+// Two algorithmic savings over the memory-resident version: slacks of outer vertices are validated
+// lazily (a stale entry -- source swallowed by the same blossom -- is a lower bound, so it is only
+// recomputed if it wins the minimum search) instead of rebuilding all slacks after every shrink or
+// expand; and label clearing / marking are lane-parallel.
+//
+// Everything is a free function over local arrays indexed by unrolled constants: keeping the
+// per-lane state out of any object whose address is taken is what keeps it in registers.
+#pragma once
+#include <stdint.h>
+
+namespace gqr {
+
+typedef int16_t i16;
+typedef int32_t i32;
+typedef uint16_t u16;
+
+static const i32 SL_INF = 0x3fffffff;
+static const u16 W_INF = 0xffff;
+enum { L_NONE = 0, L_S = 1, L_T = 2 };
+
+// shared-memory forest, capacity cap real vertices (even), nb = cap/2 blossoms, nn = cap + nb nodes
+struct Forest {
+    i16 *mate, *top;                                  // [cap]
+    i16 *base, *par, *nxt, *prv, *eu, *ev, *pu, *pv;  // [nn]
+    i16 *first;                                       // [nb]
+    i16 *stk;                                         // [2*nn]
+    i32 *yb;                                          // [nb] blossom duals
+    int8_t *label, *mark;                             // [nn]
+    int8_t *bused;                                    // [nb]
+    int cap, nb;
+};
+
+__host__ __device__ inline size_t forest_bytes(int cap) {
+    int nb = cap / 2, nn = cap + nb;
+    size_t b = (size_t)cap * 2 * 2 + (size_t)nn * 2 * 8 + (size_t)nb * 2 + (size_t)nn * 2 * 2 + (size_t)nb * 4 +
+               (size_t)nn * 2 + nb;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ Forest forest_bind(char *p, int cap) {
+    Forest f;
+    int nb = cap / 2, nn = cap + nb;
+    f.cap = cap; f.nb = nb;
+    f.yb = (i32 *)p; p += (size_t)nb * 4;
+    f.mate = (i16 *)p; p += cap * 2;
+    f.top = (i16 *)p; p += cap * 2;
+    f.base = (i16 *)p; p += nn * 2;
+    f.par = (i16 *)p; p += nn * 2;
+    f.nxt = (i16 *)p; p += nn * 2;
+    f.prv = (i16 *)p; p += nn * 2;
+    f.eu = (i16 *)p; p += nn * 2;
+    f.ev = (i16 *)p; p += nn * 2;
+    f.pu = (i16 *)p; p += nn * 2;
+    f.pv = (i16 *)p; p += nn * 2;
+    f.first = (i16 *)p; p += nb * 2;
+    f.stk = (i16 *)p; p += nn * 4;
+    f.label = (int8_t *)p; p += nn;
+    f.mark = (int8_t *)p; p += nn;
+    f.bused = (int8_t *)p;
+    return f;
+}
+
+// ---------------------------------------------------------------- lane 0 forest surgery
+__device__ __forceinline__ void rebase(const Forest &f, int x0, int a0) {
+    const int cap = f.cap;
+    int sp = 0;
+    f.stk[sp++] = (i16)x0; f.stk[sp++] = (i16)a0;
+    while (sp) {
+        int a = f.stk[--sp];
+        int B = f.stk[--sp];
+        if (B < cap || f.base[B] == a) continue;
+        int c = a;
+        while (f.par[c] != B) c = f.par[c];
+        f.stk[sp++] = (i16)c; f.stk[sp++] = (i16)a;
+        const int fst = f.first[B - cap];
+        int steps = 0;
+        for (int t = c; t != fst; t = f.prv[t]) ++steps;
+        int p = c;
+        if ((steps & 1) == 0) {
+            while (p != fst) {
+                int q1 = f.prv[p], q2 = f.prv[q1];
+                int a2 = f.eu[q2], a1 = f.ev[q2];
+                f.mate[a2] = (i16)a1; f.mate[a1] = (i16)a2;
+                f.stk[sp++] = (i16)q2; f.stk[sp++] = (i16)a2;
+                f.stk[sp++] = (i16)q1; f.stk[sp++] = (i16)a1;
+                p = q2;
+            }
+        } else {
+            while (p != fst) {
+                int q1 = f.nxt[p], q2 = f.nxt[q1];
+                int a1 = f.eu[q1], a2 = f.ev[q1];
+                f.mate[a1] = (i16)a2; f.mate[a2] = (i16)a1;
+                f.stk[sp++] = (i16)q1; f.stk[sp++] = (i16)a1;
+                f.stk[sp++] = (i16)q2; f.stk[sp++] = (i16)a2;
+                p = q2;
+            }
+        }
+        f.first[B - cap] = (i16)c;
+        f.base[B] = (i16)a;
+    }
+}
+
+__device__ __forceinline__ void augment(const Forest &f, int u, int v) {
+    int a = u, nm = v;
+    for (;;) {
+        int x = f.top[a];
+        int m = f.mate[f.base[x]];
+        rebase(f, x, a);
+        f.mate[a] = (i16)nm; f.mate[nm] = (i16)a;
+        if (m < 0) break;
+        int t = f.top[m];
+        int tpu = f.pu[t], tpv = f.pv[t];
+        rebase(f, t, tpv);
+        nm = tpv; a = tpu;
+    }
+}
+
+__device__ __forceinline__ int parent_S(const Forest &f, int x, int *tnode) {
+    int m = f.mate[f.base[x]];
+    if (m < 0) return -1;
+    int t = f.top[m];
+    *tnode = t;
+    return f.top[f.pu[t]];
+}
+
+// mark[] must be zero on entry
+__device__ __forceinline__ int shrink(const Forest &f, int u, int v) {
+    const int cap = f.cap, nb = f.nb;
+    int xu = f.top[u], xv = f.top[v];
+    for (int x = xu; x >= 0;) { f.mark[x] = 1; int t; x = parent_S(f, x, &t); }
+    int lca = xv;
+    while (!f.mark[lca]) { int t; lca = parent_S(f, lca, &t); }
+    int b = -1;
+    for (int i = 0; i < nb; ++i) if (!f.bused[i]) { b = cap + i; f.bused[i] = 1; break; }
+    if (b < 0) return -1;
+    f.nxt[lca] = (i16)lca; f.prv[lca] = (i16)lca;
+    {
+        int have = 0, bu = 0, bv = 0, first_iter = 1;
+        int x = xu;
+        while (x != lca) {
+            int t; int up = parent_S(f, x, &t);
+            int old = f.nxt[lca];
+            f.nxt[lca] = (i16)x; f.prv[x] = (i16)lca; f.nxt[x] = (i16)old; f.prv[old] = (i16)x;
+            if (!first_iter) { f.eu[x] = (i16)bu; f.ev[x] = (i16)bv; }
+            first_iter = 0;
+            old = f.nxt[lca];
+            f.nxt[lca] = (i16)t; f.prv[t] = (i16)lca; f.nxt[t] = (i16)old; f.prv[old] = (i16)t;
+            f.eu[t] = f.mate[f.base[x]]; f.ev[t] = f.base[x];
+            bu = f.pu[t]; bv = f.pv[t];
+            have = 1;
+            x = up;
+        }
+        if (have) { f.eu[lca] = (i16)bu; f.ev[lca] = (i16)bv; }
+    }
+    {
+        int tail = f.prv[lca];
+        f.eu[tail] = (i16)u; f.ev[tail] = (i16)v;
+        int x = xv;
+        while (x != lca) {
+            int t; int up = parent_S(f, x, &t);
+            f.nxt[tail] = (i16)x; f.prv[x] = (i16)tail;
+            f.eu[x] = f.base[x]; f.ev[x] = f.mate[f.base[x]];
+            f.nxt[x] = (i16)t; f.prv[t] = (i16)x; f.nxt[t] = (i16)lca; f.prv[lca] = (i16)t;
+            f.eu[t] = f.pv[t]; f.ev[t] = f.pu[t];
+            tail = t;
+            x = up;
+        }
+    }
+    f.first[b - cap] = (i16)lca;
+    f.base[b] = f.base[lca];
+    f.par[b] = -1;
+    f.yb[b - cap] = 0;
+    f.label[b] = L_S;
+    int c = lca;
+    do { f.par[c] = (i16)b; c = f.nxt[c]; } while (c != lca);
+    return b;
+}
+
+// relabel the children of T blossom b (top[] of its vertices already points at them)
+__device__ __forceinline__ void expand_relabel(const Forest &f, int b) {
+    const int cap = f.cap;
+    const int fst = f.first[b - cap];
+    const int c = f.top[f.pv[b]];
+    int steps = 0;
+    for (int t = c; t != fst; t = f.prv[t]) ++steps;
+    int x = fst;
+    do { f.label[x] = L_NONE; int nx = f.nxt[x]; f.par[x] = -1; x = nx; } while (x != fst);
+    f.label[c] = L_T; f.pu[c] = f.pu[b]; f.pv[c] = f.pv[b];
+    int p = c;
+    if ((steps & 1) == 0) {
+        while (p != fst) {
+            int s = f.prv[p], t = f.prv[s];
+            f.label[s] = L_S;
+            f.label[t] = L_T; f.pu[t] = f.ev[t]; f.pv[t] = f.eu[t];
+            p = t;
+        }
+    } else {
+        while (p != fst) {
+            int s = f.nxt[p], t = f.nxt[s];
+            f.label[s] = L_S;
+            f.label[t] = L_T; f.pu[t] = f.eu[s]; f.pv[t] = f.ev[s];
+            p = t;
+        }
+    }
+    f.bused[b - cap] = 0;
+    f.label[b] = L_NONE;
+}
+
+// ---------------------------------------------------------------- main
+// yinit[k] = minimum weight incident to vertex lane + 32k (undoubled); n even; W row stride wstride.
+// Returns 0 ok, 1 no perfect matching, 2 blossom ids exhausted, 3 step guard.  mate[] ends in f.mate.
+template <int K>
+__device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int wstride, const int n,
+                                     const int lane, const uint32_t (&yinit)[K]) {
+    const int cap = f.cap, nb = f.nb, nn = cap + nb;
+    i32 y[K], sl[K];
+    int slfrom[K], vtop[K], vlab[K];
+
+#define GQR_SEL(arr, u, out)                                           \
+    {                                                                  \
+        int sel_ = arr[0];                                             \
+        _Pragma("unroll") for (int k_ = 1; k_ < K; ++k_) if (((u) >> 5) == k_) sel_ = arr[k_]; \
+        out = __shfl_sync(0xffffffffu, sel_, (u) & 31);                \
+    }
+#define GQR_SCAN(u_)                                                   \
+    {                                                                  \
+        const int su_ = (u_);                                          \
+        const int tu_ = f.top[su_];                                    \
+        i32 yu_;                                                       \
+        GQR_SEL(y, su_, yu_);                                          \
+        const u16 *row_ = W + su_ * wstride;                           \
+        _Pragma("unroll") for (int k_ = 0; k_ < K; ++k_) {             \
+            const int v_ = lane + 32 * k_;                             \
+            if (v_ < n && vtop[k_] != tu_) {                           \
+                u16 wt_ = row_[v_];                                    \
+                if (wt_ != W_INF) {                                    \
+                    i32 s_ = 2 * (i32)wt_ - yu_ - y[k_];               \
+                    if (s_ < sl[k_]) { sl[k_] = s_; slfrom[k_] = su_; } \
+                }                                                      \
+            }                                                          \
+        }                                                              \
+    }
+#define GQR_SCAN_WHERE(pred)                                           \
+    {                                                                  \
+        _Pragma("unroll") for (int kk_ = 0; kk_ < K; ++kk_) {          \
+            unsigned m_ = __ballot_sync(0xffffffffu, pred[kk_]);       \
+            while (m_) {                                               \
+                int b_ = __ffs(m_) - 1;                                \
+                m_ &= m_ - 1;                                          \
+                GQR_SCAN(32 * kk_ + b_);                               \
+            }                                                          \
+        }                                                              \
+    }
+
+    for (int x = lane; x < nn; x += 32) { f.base[x] = (i16)(x < cap ? x : -1); f.par[x] = -1; f.label[x] = L_NONE; f.mark[x] = 0; }
+    for (int i = lane; i < nb; i += 32) f.bused[i] = 0;
+    unsigned freebits = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int v = lane + 32 * k;
+        vtop[k] = v; vlab[k] = L_NONE; sl[k] = SL_INF; slfrom[k] = -1;
+        y[k] = yinit[k] == (uint32_t)W_INF ? 0 : (i32)yinit[k];
+        if (v < n) { f.mate[v] = -1; f.top[v] = (i16)v; freebits |= 1u << k; }
+    }
+    __syncwarp();
+    // ---- greedy matching along tight edges
+    for (int u = 0; u < n; ++u) {
+        unsigned ufree = (__shfl_sync(0xffffffffu, freebits, u & 31) >> (u >> 5)) & 1u;
+        if (!ufree) continue;
+        i32 yu;
+        GQR_SEL(y, u, yu);
+        const u16 *row = W + u * wstride;
+        int found = -1;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int v = lane + 32 * k;
+            bool ok = false;
+            if (found < 0 && v < n && v != u && ((freebits >> k) & 1u)) {
+                u16 wt = row[v];
+                ok = wt != W_INF && 2 * (i32)wt - yu - y[k] == 0;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (found < 0 && m) found = 32 * k + __ffs(m) - 1;
+        }
+        if (found >= 0) {
+            if (lane == 0) { f.mate[u] = (i16)found; f.mate[found] = (i16)u; }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int v = lane + 32 * k;
+                if (v == u || v == found) freebits &= ~(1u << k);
+            }
+        }
+    }
+    __syncwarp();
+    // ---- phases: one alternating tree per free vertex
+    for (int root = 0; root < n; ++root) {
+        unsigned rfree = (__shfl_sync(0xffffffffu, freebits, root & 31) >> (root >> 5)) & 1u;
+        if (!rfree) continue;
+        for (int x = lane; x < nn; x += 32) f.label[x] = L_NONE;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { vlab[k] = L_NONE; sl[k] = SL_INF; slfrom[k] = -1; }
+        __syncwarp();
+        if (lane == 0) f.label[root] = L_S;
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (lane + 32 * k == root) vlab[k] = L_S;
+        __syncwarp();
+        GQR_SCAN(root);
+        for (int guard = 0;; ++guard) {
+            if (guard > 8 * nn + 64) return 3;
+            // ---- minimum-slack event: key = delta << 10 | type << 8 | arg
+            unsigned best = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int v = lane + 32 * k;
+                if (v < n && sl[k] < SL_INF) {
+                    if (vlab[k] == L_NONE) best = min(best, ((unsigned)sl[k] << 10) | (unsigned)v);
+                    else if (vlab[k] == L_S) best = min(best, ((unsigned)(sl[k] >> 1) << 10) | 0x100u | (unsigned)v);
+                }
+            }
+            for (int i = lane; i < nb; i += 32)
+                if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] == L_T)
+                    best = min(best, ((unsigned)(f.yb[i] >> 1) << 10) | 0x200u | (unsigned)i);
+            best = __reduce_min_sync(0xffffffffu, best);
+            if (best == 0xffffffffu) return 1;
+            const i32 delta = (i32)(best >> 10);
+            const int type = (best >> 8) & 3;
+            const int arg = best & 0xff;
+            int src = -1;
+            if (type != 2) GQR_SEL(slfrom, arg, src);
+            if (type == 1 && f.top[src] == f.top[arg]) {
+                // lazy validation: the source was swallowed by the same blossom -> recompute the exact
+                // slack of outer vertex arg towards outer vertices of other nodes, then search again
+                const int tv = f.top[arg];
+                i32 yv;
+                GQR_SEL(y, arg, yv);
+                const u16 *row = W + arg * wstride;
+                unsigned long long bb = ~0ull;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int u = lane + 32 * k;
+                    if (u < n && vlab[k] == L_S && vtop[k] != tv) {
+                        u16 wt = row[u];
+                        if (wt != W_INF) {
+                            i32 s = 2 * (i32)wt - yv - y[k];
+                            unsigned long long key = ((unsigned long long)(unsigned)s << 16) | (unsigned)u;
+                            if (key < bb) bb = key;
+                        }
+                    }
+                }
+                unsigned hi = (unsigned)(bb >> 32), lo = (unsigned)bb;
+                unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+                unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+                bb = ((unsigned long long)mh << 32) | ml;
+                const i32 ns = bb == ~0ull ? SL_INF : (i32)(bb >> 16);
+                const int nf = bb == ~0ull ? -1 : (int)(bb & 0xffff);
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (lane + 32 * k == arg) { sl[k] = ns; slfrom[k] = nf; }
+                continue;
+            }
+            // ---- dual update
+            if (delta) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (vlab[k] == L_S) { y[k] += delta; if (sl[k] < SL_INF) sl[k] -= 2 * delta; }
+                    else if (vlab[k] == L_T) y[k] -= delta;
+                    else if (sl[k] < SL_INF) sl[k] -= delta;
+                }
+                for (int i = lane; i < nb; i += 32)
+                    if (f.bused[i] && f.par[cap + i] < 0) {
+                        if (f.label[cap + i] == L_S) f.yb[i] += 2 * delta;
+                        else if (f.label[cap + i] == L_T) f.yb[i] -= 2 * delta;
+                    }
+                __syncwarp();
+            }
+            bool news[K];
+            if (type == 0) {
+                const int v = arg, u = src;
+                const int t = f.top[v];
+                const int m = f.mate[f.base[t]];
+                if (m < 0) {
+                    if (lane == 0) augment(f, u, v);
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int x = lane + 32 * k;
+                        if (x == root || x == v) freebits &= ~(1u << k);
+                    }
+                    break;
+                }
+                const int s = f.top[m];
+                if (lane == 0) { f.label[t] = L_T; f.pu[t] = (i16)u; f.pv[t] = (i16)v; f.label[s] = L_S; }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    news[k] = false;
+                    if (vtop[k] == t) vlab[k] = L_T;
+                    else if (vtop[k] == s && lane + 32 * k < n) { vlab[k] = L_S; news[k] = true; }
+                }
+            } else if (type == 1) {
+                const int v = arg, u = src;
+                for (int x = lane; x < nn; x += 32) f.mark[x] = 0;
+                __syncwarp();
+                int b = 0;
+                if (lane == 0) b = shrink(f, u, v);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b < 0) return 2;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    news[k] = false;
+                    const int x = lane + 32 * k;
+                    if (x < n && f.par[vtop[k]] == b) {
+                        news[k] = vlab[k] == L_T;   // inner vertices turn outer: they must be offered
+                        vtop[k] = b; vlab[k] = L_S;
+                        f.top[x] = (i16)b;
+                    }
+                }
+                __syncwarp();
+            } else {
+                const int b = cap + arg;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int x = lane + 32 * k;
+                    if (x < n && vtop[k] == b) {
+                        int c = x;
+                        while (f.par[c] != b) c = f.par[c];
+                        vtop[k] = c;
+                        f.top[x] = (i16)c;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) expand_relabel(f, b);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int x = lane + 32 * k;
+                    news[k] = false;
+                    if (x < n) {
+                        int nl = f.label[vtop[k]];
+                        news[k] = nl == L_S && vlab[k] != L_S;
+                        vlab[k] = nl;
+                    }
+                }
+            }
+            GQR_SCAN_WHERE(news);
+        }
+    }
+    return 0;
+#undef GQR_SEL
+#undef GQR_SCAN
+#undef GQR_SCAN_WHERE
+}
+
+}  // namespace gqr

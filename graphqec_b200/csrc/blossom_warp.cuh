@@ -47,7 +47,7 @@ __device__ __forceinline__ int gq_bcast(int v, int src) { return __shfl_sync(0xf
 
 #ifdef GQ_HOST_SIM
 #define GQ_COUNT(x) (++gq_counters[x])
-static long long gq_counters[8];  // 0 shrink, 1 expand, 2 nested shrink, 3 augment through blossom, 4 odd-slack
+static long long gq_counters[16];  // 0 shrink, 1 expand, 2 nested shrink, 3 augment through blossom, 4 odd-slack
 #else
 #define GQ_COUNT(x) ((void)0)
 #endif
@@ -140,6 +140,7 @@ struct Solver {
 
     // ---- lane-parallel: offer vertex u (just became outer) to every vertex outside its node
     GQ_DEV void scan(int u) {
+        GQ_COUNT(5);
         const int tu = w.top[u];
         const i32 yu = w.y[u];
         const u16 *row = w.W + u * w.wstride;
@@ -161,6 +162,7 @@ struct Solver {
     }
 
     GQ_DEV void rescan_all() {
+        GQ_COUNT(6);
         for (int v = GQ_LANE; v < n; v += GQ_NLANES) { w.sl[v] = SL_INF; w.slfrom[v] = -1; }
         GQ_SYNC();
         for (int u = 0; u < n; ++u) {
@@ -398,6 +400,7 @@ struct Solver {
         // ---- phases
         for (int root = 0; root < n; ++root) {
             if (w.mate[root] >= 0) continue;
+            GQ_COUNT(7);
             for (int x = GQ_LANE; x < nn; x += GQ_NLANES) w.label[x] = L_NONE;
             for (int v = GQ_LANE; v < n; v += GQ_NLANES) { w.sl[v] = SL_INF; w.slfrom[v] = -1; }
             GQ_SYNC();
@@ -430,6 +433,7 @@ struct Solver {
                     }
                 }
                 best = gq_warp_min_u64(best);
+                GQ_COUNT(8);
                 if (best == ~0ull) return 1;
                 const i32 delta = (i32)(best >> 20);
                 const int type = (int)((best >> 16) & 0xf);

@@ -20,6 +20,7 @@
 #include <queue>
 #include <thread>
 
+#include "blossom_regs.cuh"
 #include "blossom_warp.cuh"
 #include "gq_common.h"
 
@@ -157,6 +158,146 @@ __global__ void __launch_bounds__(256) match_kernel(MatchArgs a) {
                             pm ^= bobs[di] ^ bobs[dj];
                             wt += (int)s;
                             if (corr_row) { walk_path(a, di, a.D, corr_row); walk_path(a, dj, a.D, corr_row); }
+                        }
+                    }
+                }
+                pm = __reduce_xor_sync(0xffffffffu, pm);
+                wt = __reduce_add_sync(0xffffffffu, wt);
+            }
+        }
+        if (lane == 0) {
+            a.pred[shot * a.OW] = rc == 0 ? pm : 0u;
+            for (uint32_t w = 1; w < a.OW; ++w) a.pred[shot * a.OW + w] = 0u;
+            if (a.weight_out) a.weight_out[shot] = rc == 0 ? wt : -1;
+            if (a.flags_out) a.flags_out[shot] = (uint8_t)(rc == 0 ? 0 : (rc == 1 ? 1 : 2));
+        }
+        __syncwarp();
+    }
+}
+
+
+// ---- fast tier: register-resident solver (blossom_regs.cuh), forest in shared memory, W in an
+// L2-resident scratch; handles shots with fewer than 32*K defects, the rest go to the overflow list
+template <int K>
+__global__ void __launch_bounds__(256, 4) match_fast_kernel(MatchArgs a) {
+    extern __shared__ __align__(16) char smem[];
+    constexpr int CAP = 32 * K;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t N = a.D + 1;
+    const size_t per_warp = gqr::forest_bytes(CAP) + (size_t)CAP * 4;
+    char *mem = smem + (size_t)wib * per_warp;
+    const gqr::Forest F = gqr::forest_bind(mem, CAP);
+    uint16_t *def = (uint16_t *)(mem + gqr::forest_bytes(CAP));
+    uint16_t *bd = def + CAP;
+    uint16_t *Wm = (uint16_t *)(a.ws + warp * a.ws_stride);
+    const uint16_t *brow = a.dist + (size_t)a.D * N;
+    const uint8_t *bobs = a.pobs + (size_t)a.D * N;
+
+    for (uint64_t item = warp; item < a.nitems; item += nwarps) {
+        const uint64_t shot = item;
+        const uint32_t *row = a.dets + shot * a.DW;
+        int n0 = 0;
+        for (uint32_t w0 = 0; w0 < a.DW; w0 += 32) {
+            uint32_t wi = w0 + lane;
+            uint32_t word = wi < a.DW ? row[wi] : 0u;
+            if (wi == a.DW - 1 && (a.D & 31)) word &= (1u << (a.D & 31)) - 1;
+            int cnt = __popc(word);
+            int pre = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += t;
+            }
+            int tot = __shfl_sync(0xffffffffu, pre, 31);
+            int pos = n0 + pre - cnt;
+            while (word) {
+                int b = __ffs(word) - 1;
+                word &= word - 1;
+                if (pos < CAP) def[pos] = (uint16_t)(wi * 32 + b);
+                ++pos;
+            }
+            n0 += tot;
+        }
+        __syncwarp();
+        if (n0 > CAP - 1) {
+            if (lane == 0) {
+                uint32_t idx = atomicAdd(&a.overflow[0], 1u);
+                atomicMax(&a.overflow[1], (uint32_t)n0);
+                if (idx < a.overflow_cap) a.overflow[2 + idx] = (uint32_t)shot;
+            }
+            continue;
+        }
+        uint32_t pm = 0;
+        int wt = 0, rc = 0;
+        if (n0 > 0) {
+            const int n = n0 + (n0 & 1);
+            const int stride = n + 1;
+            uint32_t dj[K], bj[K], ymin[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int j = lane + 32 * k;
+                dj[k] = j < n0 ? def[j] : 0u;
+                bj[k] = j < n0 ? brow[dj[k]] : 0xFFFFu;
+                if (j < n0) bd[j] = (uint16_t)bj[k];
+                ymin[k] = 0xFFFFu;
+            }
+            __syncwarp();
+            for (int i = 0; i < n0; ++i) {
+                const uint32_t di = def[i];
+                const uint32_t bi = bd[i];
+                const uint16_t *drow = a.dist + (size_t)di * N;
+                uint16_t *wrow = Wm + i * stride;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int j = lane + 32 * k;
+                    if (j < n0) {
+                        uint32_t d = drow[dj[k]];
+                        uint32_t s = (bi == 0xFFFFu || bj[k] == 0xFFFFu) ? 0xFFFFu : min(bi + bj[k], 0xFFFEu);
+                        uint32_t w = j == i ? 0xFFFFu : min(d, s);
+                        wrow[j] = (uint16_t)w;
+                        ymin[k] = min(ymin[k], w);
+                    }
+                }
+                if (n != n0 && lane == 0) wrow[n0] = (uint16_t)bi;
+            }
+            if (n != n0) {
+                uint32_t mb = 0xFFFFu;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int j = lane + 32 * k;
+                    if (j < n0) { Wm[n0 * stride + j] = (uint16_t)bj[k]; ymin[k] = min(ymin[k], bj[k]); mb = min(mb, bj[k]); }
+                }
+                mb = __reduce_min_sync(0xffffffffu, mb);
+                if (lane == 0) Wm[n0 * stride + n0] = 0xFFFFu;
+#pragma unroll
+                for (int k = 0; k < K; ++k) if (lane + 32 * k == n0) ymin[k] = mb;
+            }
+            __syncwarp();
+            rc = gqr::solve<K>(F, Wm, stride, n, lane, ymin);
+            __syncwarp();
+            if (rc == 0) {
+                uint32_t *corr_row = a.corr_out ? a.corr_out + shot * a.EW : nullptr;
+                for (int i = lane; i < n0; i += 32) {
+                    int j = F.mate[i];
+                    const uint32_t di = def[i];
+                    if (j == n0) {
+                        pm ^= bobs[di];
+                        wt += bd[i];
+                        if (corr_row) walk_path(a, di, a.D, corr_row);
+                    } else if (j > i) {
+                        const uint32_t dj2 = def[j];
+                        uint32_t d = a.dist[(size_t)dj2 * N + di];
+                        uint32_t s = (bd[i] == 0xFFFFu || bd[j] == 0xFFFFu) ? 0xFFFFu : (uint32_t)bd[i] + bd[j];
+                        if (d <= s) {
+                            pm ^= a.pobs[(size_t)dj2 * N + di];
+                            wt += (int)d;
+                            if (corr_row) walk_path(a, di, dj2, corr_row);
+                        } else {
+                            pm ^= bobs[di] ^ bobs[dj2];
+                            wt += (int)s;
+                            if (corr_row) { walk_path(a, di, a.D, corr_row); walk_path(a, dj2, a.D, corr_row); }
                         }
                     }
                 }
@@ -332,10 +473,13 @@ int gq_matching_create(gq_dec *dec) {
         GQ_CUDA(cudaMalloc((void **)&dec->d_adj_edge, std::max<size_t>(adj_edge.size(), 1) * 4));
         GQ_CUDA(cudaMemcpy(dec->d_adj_edge, adj_edge.data(), adj_edge.size() * 4, cudaMemcpyHostToDevice));
     }
-    // ---- fast-tier workspaces: 2 blocks of 8 warps per SM
-    dec->nwarps_fast = dem->num_sms * 2 * 8;
-    dec->ws_fast_bytes = warp_ws_bytes(fast);
+    // ---- fast tier: register-resident solver, K = 4 slots per lane (< 128 defects), 3 blocks of
+    // 8 warps per SM; its only global workspace is the dense weight matrix of each warp
+    dec->fast_cap = 128;
+    dec->nwarps_fast = dem->num_sms * 4 * 8;
+    dec->ws_fast_bytes = ((size_t)128 * 129 * 2 + 255) & ~(size_t)255;
     GQ_CUDA(cudaMalloc(&dec->d_ws_fast, dec->ws_fast_bytes * dec->nwarps_fast));
+    GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     dec->overflow_cap = 1u << 20;
     GQ_CUDA(cudaMalloc((void **)&dec->d_overflow, (2 + (size_t)dec->overflow_cap) * 4));
     return GQ_OK;
@@ -374,7 +518,8 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
         b.ws = (char *)dec->d_ws_fast; b.ws_stride = dec->ws_fast_bytes;
         b.overflow = dec->d_overflow; b.overflow_cap = dec->overflow_cap;
         int blocks = (int)std::min<uint64_t>((ns + 7) / 8, (uint64_t)dec->nwarps_fast / 8);
-        match_kernel<<<blocks, 256, 0, dem->stream>>>(b);
+        size_t smem = 8 * (gqr::forest_bytes(128) + 128 * 4);
+        match_fast_kernel<4><<<blocks, 256, smem, dem->stream>>>(b);
         GQ_CUDA(cudaGetLastError());
         ++*launches;
         uint32_t ovf[2];

@@ -27,5 +27,5 @@ extern "C" int hostsim_solve(int n, const uint16_t *W, int16_t *mate_out, long l
 }
 
 extern "C" void hostsim_counters(long long *out) {
-    for (int i = 0; i < 8; ++i) out[i] = gq_counters[i];
+    for (int i = 0; i < 16; ++i) out[i] = gq_counters[i];
 }

@@ -48,3 +48,32 @@ def test_unsupported_decoder_raises():
     th = ThresholdLAB(configurations=[{"distance": 3}], code=RepetitionCode, error_rates=[0.1], decoder="mwpf")
     with pytest.raises(NotImplementedError):
         th.collect_stats(max_shots=100)
+
+
+def test_sinter_style_adapters():
+    """The plug-in seam of the reference (custom_decoders): compile_decoder_for_dem / decode_shots_bit_packed."""
+    from graphqec_b200.sinter_compat import B200Decoder, B200Sampler
+    from graphqec_b200.stats import Task
+
+    code = RotatedSurfaceCode(distance=3, depolarize1_rate=0.01, depolarize2_rate=0.01)
+    code.build_memory_circuit(number_of_rounds=3)
+    dem = code.memory_circuit.detector_error_model(decompose_errors=True)
+    compiled = B200Decoder().compile_decoder_for_dem(dem=dem)
+    dets, obs = po.sample(dem, 1, 4000)
+    pred = compiled.decode_shots_bit_packed(bit_packed_detection_event_data=dets)
+    assert pred.shape == (4000, 1) and pred.dtype == np.uint8
+    ref = po.MwpmOracle(dem).decode_batch(dets, nthreads=4)
+    assert (pred[:, 0] == ref).mean() > 0.97           # equal up to ties between minimum-weight matchings
+    # DEM given as Stim text works too
+    from graphqec_b200 import DetectorErrorModel
+    again = B200Decoder().compile_decoder_for_dem(dem=DetectorErrorModel.from_text(str(dem)))
+    assert (again.decode_shots_bit_packed(bit_packed_detection_event_data=dets) == pred).all()
+    st = B200Sampler().compiled_sampler_for_task(Task(circuit=code.memory_circuit)).sample(10000)
+    assert st.shots >= 10000 and 0 < st.errors < st.shots // 10
+
+
+def test_bposd_name_runs_min_sum_bp():
+    th = ThresholdLAB(configurations=[{"distance": 3}], code=RotatedSurfaceCode, error_rates=[0.002], decoder="bposd")
+    th.collect_stats(max_shots=20000, max_errors=10**9)
+    st = th.samples[0]
+    assert st.shots == 20000 and st.errors < 2000

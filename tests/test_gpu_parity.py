@@ -302,3 +302,55 @@ def test_north_star_dem_on_device():
     assert abs(demh.info.sum_p - 36.94) < 0.01 and demh.info.num_classes == 36
     gi = dech.graph_info
     assert gi.num_edges == 6930 and gi.num_boundary_edges == 360
+
+
+# ------------------------------------------------------------------------------------------ K3b
+def _bp_case(name, **params):
+    dem, demh, _ = case(name)
+    return dem, demh, be.DecoderHandle(demh, be.BP_MINSUM, **params)
+
+
+@pytest.mark.parametrize("name,nshots", [("rot3", 300), ("steane", 300), ("rot5", 120)])
+def test_bp_matches_oracle_bit_for_bit(name, nshots):
+    """Same schedule, same fp32 summation order as oracle/bp_oracle.c: identical decisions and iteration counts."""
+    dem, demh, bp = _bp_case(name, bp_max_iter=25, bp_alpha=0.9)
+    orc = po.BpOracle(dem, max_iter=25, alpha=0.9)
+    dets, obs = demh.sample(17, 0, nshots)
+    pred, iters, flags, corr = bp.decode(dets, want_weights=True, want_flags=True, want_corrections=True)
+    bits = np.unpackbits(b8(dets, dem.num_detectors), axis=1, bitorder="little")[:, : dem.num_detectors]
+    cb = np.unpackbits(corr.cpu().numpy().view(np.uint8).reshape(nshots, -1), axis=1, bitorder="little")[:, : dem.num_errors]
+    H, L = dem.dense_check_matrices()
+    it_gpu = iters.cpu().numpy()
+    nconv = 0
+    for s in range(nshots):
+        e, it = orc.decode(bits[s])
+        assert it == it_gpu[s], (s, it, it_gpu[s])
+        assert (e == cb[s]).all()
+        if it > 0:
+            nconv += 1
+            assert ((H @ cb[s]) % 2 == bits[s]).all()          # converged output reproduces the syndrome
+    p32 = pred.cpu().numpy().view(np.uint32)[:, 0]
+    assert ((cb @ L.T) % 2 == (p32[:, None] & 1)).all()          # prediction = L.e
+    assert ((flags.cpu().numpy() == 0) == (it_gpu > 0)).all()
+    assert nconv > 0.5 * nshots
+
+
+def test_bp_on_bivariate_bicycle_code():
+    """BASELINE configs[4] in miniature: BB [[72,12,6]], hyperedge DEM, min-sum BP through the fused path."""
+    code = gq.BivariateBicycleCode(L1=6, L2=6, a1=3, a2=1, a3=2, b1=3, b2=1, b3=2, depolarize1_rate=0.001, depolarize2_rate=0.001)
+    code.build_memory_circuit(number_of_rounds=2, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model()
+    assert np.diff(dem.det_indptr.astype(int)).max() > 2          # genuinely non-matchable
+    demh = be.DemHandle(dem, device=0)
+    bp = be.DecoderHandle(demh, be.BP_MINSUM, bp_max_iter=30)
+    n = 8 * demh.tile_shots
+    dets, obs = demh.sample(3, 0, n)
+    pred, iters, flags = bp.decode(dets, want_weights=True, want_flags=True)
+    conv = (flags == 0)
+    assert conv.float().mean().item() > 0.6
+    # converged shots at this low error rate are almost always decoded correctly
+    good = ((pred == obs).all(dim=1) & conv).sum().item() / max(1, conv.sum().item())
+    assert good > 0.95
+    shots, errors, _ = bp.collect(3, 0, n, 0)
+    assert shots == n and errors == int((pred != obs).any(dim=1).sum().item())
+    bp.close(); demh.close()

@@ -133,7 +133,7 @@ def test_decoder_matching_core_is_exact_on_host(hostsim):
         big = (int(w.max()) + 1) * (n + 2)
         tot, m2 = po.max_weight_matching(np.where(np.eye(n, dtype=bool), 0, big - w.astype(np.int64)))
         assert wt.value == sum(int(w[i, m2[i]]) for i in range(n) if m2[i] > i)
-    c = (ctypes.c_longlong * 8)()
+    c = (ctypes.c_longlong * 16)()
     hostsim.hostsim_counters(c)
     assert c[0] > 100 and c[1] > 10 and c[2] > 10  # shrink, expand and nested blossoms were exercised
     assert c[4] == 0                               # slack parity invariant never broken
