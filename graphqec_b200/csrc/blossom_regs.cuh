@@ -17,6 +17,12 @@
 #pragma once
 #include <stdint.h>
 
+#ifdef GQ_STATS
+#define GQ_STAT(i) do { if (lane == 0) atomicAdd(&gq_stats[i], 1ull); } while (0)
+#else
+#define GQ_STAT(i) do { } while (0)
+#endif
+
 namespace gqr {
 
 typedef int16_t i16;
@@ -32,6 +38,7 @@ struct Forest {
     i16 *mate, *top;                                  // [cap]
     i16 *base, *par, *nxt, *prv, *eu, *ev, *pu, *pv;  // [nn]
     i16 *first;                                       // [nb]
+    i16 *troot;                                       // [nn] root vertex of the tree a labelled node is in
     i16 *stk;                                         // [2*nn]
     i32 *yb;                                          // [nb] blossom duals
     int8_t *label, *mark;                             // [nn]
@@ -41,7 +48,7 @@ struct Forest {
 
 __host__ __device__ inline size_t forest_bytes(int cap) {
     int nb = cap / 2, nn = cap + nb;
-    size_t b = (size_t)cap * 2 * 2 + (size_t)nn * 2 * 8 + (size_t)nb * 2 + (size_t)nn * 2 * 2 + (size_t)nb * 4 +
+    size_t b = (size_t)cap * 2 * 2 + (size_t)nn * 2 * 9 + (size_t)nb * 2 + (size_t)nn * 2 * 2 + (size_t)nb * 4 +
                (size_t)nn * 2 + nb;
     return (b + 15) & ~(size_t)15;
 }
@@ -62,6 +69,7 @@ __device__ __forceinline__ Forest forest_bind(char *p, int cap) {
     f.pu = (i16 *)p; p += nn * 2;
     f.pv = (i16 *)p; p += nn * 2;
     f.first = (i16 *)p; p += nb * 2;
+    f.troot = (i16 *)p; p += nn * 2;
     f.stk = (i16 *)p; p += nn * 4;
     f.label = (int8_t *)p; p += nn;
     f.mark = (int8_t *)p; p += nn;
@@ -116,6 +124,25 @@ __device__ __forceinline__ void augment(const Forest &f, int u, int v) {
         int m = f.mate[f.base[x]];
         rebase(f, x, a);
         f.mate[a] = (i16)nm; f.mate[nm] = (i16)a;
+        if (m < 0) break;
+        int t = f.top[m];
+        int tpu = f.pu[t], tpv = f.pv[t];
+        rebase(f, t, tpv);
+        nm = tpv; a = tpu;
+    }
+}
+
+// one side of an augmentation between two trees: flip the path from outer vertex u to its root and
+// point u at its new mate nm (the caller's other half sets mate[nm])
+__device__ __forceinline__ void augment_half(const Forest &f, int u, int nm0) {
+    int a = u, nm = nm0, first = 1;
+    for (;;) {
+        int x = f.top[a];
+        int m = f.mate[f.base[x]];
+        rebase(f, x, a);
+        f.mate[a] = (i16)nm;
+        if (!first) f.mate[nm] = (i16)a;
+        first = 0;
         if (m < 0) break;
         int t = f.top[m];
         int tpu = f.pu[t], tpv = f.pv[t];
@@ -222,6 +249,8 @@ template <int K>
 __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int wstride, const int n,
                                      const int lane, const uint32_t (&yinit)[K]) {
     const int cap = f.cap, nb = f.nb, nn = cap + nb;
+    const int kmax = (n + 31) >> 5;   // slots in use (uniform)
+    int bhi = 0;                      // blossom ids in use are below cap + bhi
     i32 y[K], sl[K];
     int slfrom[K], vtop[K], vlab[K];
 
@@ -240,7 +269,7 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
         const u16 *row_ = W + su_ * wstride;                           \
         _Pragma("unroll") for (int k_ = 0; k_ < K; ++k_) {             \
             const int v_ = lane + 32 * k_;                             \
-            if (v_ < n && vtop[k_] != tu_) {                           \
+            if (k_ < kmax && v_ < n && vtop[k_] != tu_) {              \
                 u16 wt_ = row_[v_];                                    \
                 if (wt_ != W_INF) {                                    \
                     i32 s_ = 2 * (i32)wt_ - yu_ - y[k_];               \
@@ -252,11 +281,11 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
 #define GQR_SCAN_WHERE(pred)                                           \
     {                                                                  \
         _Pragma("unroll") for (int kk_ = 0; kk_ < K; ++kk_) {          \
-            unsigned m_ = __ballot_sync(0xffffffffu, pred[kk_]);       \
+            unsigned m_ = kk_ < kmax ? __ballot_sync(0xffffffffu, pred[kk_]) : 0u; \
             while (m_) {                                               \
                 int b_ = __ffs(m_) - 1;                                \
                 m_ &= m_ - 1;                                          \
-                GQR_SCAN(32 * kk_ + b_);                               \
+                GQ_STAT(6); GQR_SCAN(32 * kk_ + b_);                   \
             }                                                          \
         }                                                              \
     }
@@ -284,7 +313,7 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
         for (int k = 0; k < K; ++k) {
             const int v = lane + 32 * k;
             bool ok = false;
-            if (found < 0 && v < n && v != u && ((freebits >> k) & 1u)) {
+            if (k < kmax && found < 0 && v < n && v != u && ((freebits >> k) & 1u)) {
                 u16 wt = row[v];
                 ok = wt != W_INF && 2 * (i32)wt - yu - y[k] == 0;
             }
@@ -301,6 +330,10 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
         }
     }
     __syncwarp();
+    GQ_STAT(7);
+#ifdef GQ_STATS
+    { int nf_ = __reduce_add_sync(0xffffffffu, __popc(freebits)); if (lane == 0) atomicAdd(&gq_stats[8], (unsigned long long)nf_); }
+#endif
     // ---- phases: one alternating tree per free vertex
     for (int root = 0; root < n; ++root) {
         unsigned rfree = (__shfl_sync(0xffffffffu, freebits, root & 31) >> (root >> 5)) & 1u;
@@ -321,15 +354,16 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int v = lane + 32 * k;
-                if (v < n && sl[k] < SL_INF) {
+                if (k < kmax && v < n && sl[k] < SL_INF) {
                     if (vlab[k] == L_NONE) best = min(best, ((unsigned)sl[k] << 10) | (unsigned)v);
                     else if (vlab[k] == L_S) best = min(best, ((unsigned)(sl[k] >> 1) << 10) | 0x100u | (unsigned)v);
                 }
             }
-            for (int i = lane; i < nb; i += 32)
+            for (int i = lane; i < bhi; i += 32)
                 if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] == L_T)
                     best = min(best, ((unsigned)(f.yb[i] >> 1) << 10) | 0x200u | (unsigned)i);
             best = __reduce_min_sync(0xffffffffu, best);
+            GQ_STAT(0);
             if (best == 0xffffffffu) return 1;
             const i32 delta = (i32)(best >> 10);
             const int type = (best >> 8) & 3;
@@ -337,6 +371,7 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
             int src = -1;
             if (type != 2) GQR_SEL(slfrom, arg, src);
             if (type == 1 && f.top[src] == f.top[arg]) {
+                GQ_STAT(1);
                 // lazy validation: the source was swallowed by the same blossom -> recompute the exact
                 // slack of outer vertex arg towards outer vertices of other nodes, then search again
                 const int tv = f.top[arg];
@@ -347,7 +382,7 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const int u = lane + 32 * k;
-                    if (u < n && vlab[k] == L_S && vtop[k] != tv) {
+                    if (k < kmax && u < n && vlab[k] == L_S && vtop[k] != tv) {
                         u16 wt = row[u];
                         if (wt != W_INF) {
                             i32 s = 2 * (i32)wt - yv - y[k];
@@ -371,11 +406,12 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
             if (delta) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
+                    if (k >= kmax) continue;
                     if (vlab[k] == L_S) { y[k] += delta; if (sl[k] < SL_INF) sl[k] -= 2 * delta; }
                     else if (vlab[k] == L_T) y[k] -= delta;
                     else if (sl[k] < SL_INF) sl[k] -= delta;
                 }
-                for (int i = lane; i < nb; i += 32)
+                for (int i = lane; i < bhi; i += 32)
                     if (f.bused[i] && f.par[cap + i] < 0) {
                         if (f.label[cap + i] == L_S) f.yb[i] += 2 * delta;
                         else if (f.label[cap + i] == L_T) f.yb[i] -= 2 * delta;
@@ -388,6 +424,7 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
                 const int t = f.top[v];
                 const int m = f.mate[f.base[t]];
                 if (m < 0) {
+                    GQ_STAT(4);
                     if (lane == 0) augment(f, u, v);
                     __syncwarp();
 #pragma unroll
@@ -397,6 +434,7 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
                     }
                     break;
                 }
+                GQ_STAT(2);
                 const int s = f.top[m];
                 if (lane == 0) { f.label[t] = L_T; f.pu[t] = (i16)u; f.pv[t] = (i16)v; f.label[s] = L_S; }
                 __syncwarp();
@@ -411,9 +449,11 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
                 for (int x = lane; x < nn; x += 32) f.mark[x] = 0;
                 __syncwarp();
                 int b = 0;
+                GQ_STAT(3);
                 if (lane == 0) b = shrink(f, u, v);
                 b = __shfl_sync(0xffffffffu, b, 0);
                 if (b < 0) return 2;
+                bhi = max(bhi, b - cap + 1);
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
@@ -427,6 +467,7 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
                 }
                 __syncwarp();
             } else {
+                GQ_STAT(5);
                 const int b = cap + arg;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
@@ -459,6 +500,355 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
 #undef GQR_SEL
 #undef GQR_SCAN
 #undef GQR_SCAN_WHERE
+}
+
+// ---------------------------------------------------------------- multi-tree variant
+// All free vertices grow alternating trees at once (one global dual clock D); an S-S edge between two
+// trees augments and dissolves just those two trees, every other tree keeps its labels and slacks.
+// Duals and slacks are stored against the clock, so a dual step costs nothing:
+//   vertex dual    y = yb + sg*D            (sg = +1 outer, -1 inner, 0 unlabelled)
+//   blossom dual   z = zb + 2*sg*D
+//   tm = absolute time at which the best edge into the vertex turns tight (unlabelled: D0+slack,
+//        outer: D0+slack/2) or, for an inner vertex, its frozen slack.
+// Units are quadrupled (y_u + y_v <= 4w, initial duals even) so that every event time is an integer
+// even across trees.  Entries are validated when they win the search (source still outer, other
+// node, edge tight at that time); anything else is stale -- a lower bound -- and is recomputed.
+template <int K>
+__device__ __forceinline__ int solve_mt(const Forest &f, const u16 *W, const int wstride, const int n,
+                                        const int lane, const uint32_t (&yinit)[K]) {
+    const int cap = f.cap, nb = f.nb, nn = cap + nb;
+    const int kmax = (n + 31) >> 5;
+    i32 yb[K], tm[K];
+    int slfrom[K], vtop[K], vlab[K];
+    i32 D = 0;
+    int bhi = 0;
+
+#define GQM_YACT(k_, t_) (yb[k_] + (vlab[k_] == L_S ? (t_) : (vlab[k_] == L_T ? -(t_) : 0)))
+#define GQM_SEL(arr, u, out)                                           \
+    {                                                                  \
+        int sel_ = arr[0];                                             \
+        _Pragma("unroll") for (int k_ = 1; k_ < K; ++k_) if (((u) >> 5) == k_) sel_ = arr[k_]; \
+        out = __shfl_sync(0xffffffffu, sel_, (u) & 31);                \
+    }
+#define GQM_YOF(u, t_, out)                                            \
+    {                                                                  \
+        int sel_ = GQM_YACT(0, t_);                                    \
+        _Pragma("unroll") for (int k_ = 1; k_ < K; ++k_) if (((u) >> 5) == k_) sel_ = GQM_YACT(k_, t_); \
+        out = __shfl_sync(0xffffffffu, sel_, (u) & 31);                \
+    }
+#define GQM_SCAN(u_)                                                   \
+    {                                                                  \
+        const int su_ = (u_);                                          \
+        const int tu_ = f.top[su_];                                    \
+        i32 yu_;                                                       \
+        GQM_YOF(su_, D, yu_);                                          \
+        const u16 *row_ = W + su_ * wstride;                           \
+        _Pragma("unroll") for (int k_ = 0; k_ < K; ++k_) {             \
+            if (k_ < kmax) {                                           \
+                const int v_ = lane + 32 * k_;                         \
+                if (v_ < n && vtop[k_] != tu_) {                       \
+                    u16 wt_ = row_[v_];                                \
+                    if (wt_ != W_INF) {                                \
+                        i32 s_ = 4 * (i32)wt_ - yu_ - GQM_YACT(k_, D); \
+                        i32 c_ = vlab[k_] == L_NONE ? D + s_ : (vlab[k_] == L_S ? D + (s_ >> 1) : s_); \
+                        if (c_ < tm[k_]) { tm[k_] = c_; slfrom[k_] = su_; } \
+                    }                                                  \
+                }                                                      \
+            }                                                          \
+        }                                                              \
+    }
+#define GQM_SCAN_WHERE(pred)                                           \
+    {                                                                  \
+        _Pragma("unroll") for (int kk_ = 0; kk_ < K; ++kk_) {          \
+            if (kk_ < kmax) {                                          \
+                unsigned m_ = __ballot_sync(0xffffffffu, pred[kk_]);   \
+                while (m_) {                                           \
+                    int b_ = __ffs(m_) - 1;                            \
+                    m_ &= m_ - 1;                                      \
+                    GQ_STAT(6); GQM_SCAN(32 * kk_ + b_);               \
+                }                                                      \
+            }                                                          \
+        }                                                              \
+    }
+
+    for (int x = lane; x < nn; x += 32) { f.base[x] = (i16)(x < cap ? x : -1); f.par[x] = -1; f.label[x] = L_NONE; f.mark[x] = 0; }
+    for (int i = lane; i < nb; i += 32) f.bused[i] = 0;
+    unsigned freebits = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int v = lane + 32 * k;
+        vtop[k] = v; vlab[k] = L_NONE; tm[k] = SL_INF; slfrom[k] = -1;
+        yb[k] = yinit[k] == (uint32_t)W_INF ? 0 : 2 * (i32)yinit[k];
+        if (v < n) { f.mate[v] = -1; f.top[v] = (i16)v; freebits |= 1u << k; }
+    }
+    __syncwarp();
+    // ---- greedy matching along tight edges
+    for (int u = 0; u < n; ++u) {
+        unsigned ufree = (__shfl_sync(0xffffffffu, freebits, u & 31) >> (u >> 5)) & 1u;
+        if (!ufree) continue;
+        i32 yu;
+        GQM_SEL(yb, u, yu);
+        const u16 *row = W + u * wstride;
+        int found = -1;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (k < kmax) {
+                const int v = lane + 32 * k;
+                bool ok = false;
+                if (found < 0 && v < n && v != u && ((freebits >> k) & 1u)) {
+                    u16 wt = row[v];
+                    ok = wt != W_INF && 4 * (i32)wt - yu - yb[k] == 0;
+                }
+                unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (found < 0 && m) found = 32 * k + __ffs(m) - 1;
+            }
+        }
+        if (found >= 0) {
+            if (lane == 0) { f.mate[u] = (i16)found; f.mate[found] = (i16)u; }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int v = lane + 32 * k;
+                if (v == u || v == found) freebits &= ~(1u << k);
+            }
+        }
+    }
+    int nfree = __reduce_add_sync(0xffffffffu, __popc(freebits));
+    GQ_STAT(7);
+#ifdef GQ_STATS
+    if (lane == 0) atomicAdd(&gq_stats[8], (unsigned long long)nfree);
+#endif
+    if (nfree == 0) return 0;
+    // ---- every free vertex roots a tree
+    bool news[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int v = lane + 32 * k;
+        news[k] = v < n && ((freebits >> k) & 1u);
+        if (news[k]) { vlab[k] = L_S; f.label[v] = L_S; f.troot[v] = (i16)v; }
+    }
+    __syncwarp();
+    GQM_SCAN_WHERE(news);
+
+    for (int guard = 0;; ++guard) {
+        if (guard > 24 * nn + 256) return 3;
+        // ---- earliest event: key = time << 10 | type << 8 | arg
+        unsigned best = 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (k < kmax) {
+                const int v = lane + 32 * k;
+                if (v < n && tm[k] < SL_INF && vlab[k] != L_T)
+                    best = min(best, ((unsigned)tm[k] << 10) | (vlab[k] == L_S ? 0x100u : 0u) | (unsigned)v);
+            }
+        }
+        for (int i = lane; i < bhi; i += 32)
+            if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] == L_T)
+                best = min(best, ((unsigned)(f.yb[i] >> 1) << 10) | 0x200u | (unsigned)i);
+        best = __reduce_min_sync(0xffffffffu, best);
+        GQ_STAT(0);
+        if (best == 0xffffffffu) return 1;
+        const i32 t = (i32)(best >> 10);
+        const int type = (best >> 8) & 3;
+        const int arg = best & 0xff;
+        int src = -1;
+        if (type != 2) {
+            GQM_SEL(slfrom, arg, src);
+            const int tu = f.top[src], tv = f.top[arg];
+            bool valid = f.label[tu] == L_S && tu != tv;
+            if (valid) {
+                i32 yu, yv;
+                GQM_YOF(src, t, yu);
+                GQM_YOF(arg, t, yv);
+                valid = 4 * (i32)W[src * wstride + arg] - yu - yv == 0;
+            }
+            if (!valid) {
+                GQ_STAT(1);
+                // stale entry: recompute the best edge from the current outer vertices into arg
+                i32 yv;
+                GQM_YOF(arg, D, yv);
+                const u16 *row = W + arg * wstride;
+                unsigned long long bb = ~0ull;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (k < kmax) {
+                        const int u = lane + 32 * k;
+                        if (u < n && vlab[k] == L_S && vtop[k] != tv) {
+                            u16 wt = row[u];
+                            if (wt != W_INF) {
+                                i32 s = 4 * (i32)wt - yv - (yb[k] + D);
+                                unsigned long long key = ((unsigned long long)(unsigned)s << 16) | (unsigned)u;
+                                if (key < bb) bb = key;
+                            }
+                        }
+                    }
+                }
+                unsigned hi = (unsigned)(bb >> 32), lo = (unsigned)bb;
+                unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+                unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+                bb = ((unsigned long long)mh << 32) | ml;
+                const i32 s = (i32)(bb >> 16);
+                const i32 nt = bb == ~0ull ? SL_INF : (type == 0 ? D + s : D + (s >> 1));
+                const int nf = bb == ~0ull ? -1 : (int)(bb & 0xffff);
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (lane + 32 * k == arg) { tm[k] = nt; slfrom[k] = nf; }
+                continue;
+            }
+        }
+        D = t;
+#pragma unroll
+        for (int k = 0; k < K; ++k) news[k] = false;
+        if (type == 0) {
+            GQ_STAT(2);
+            // ---- grow: unlabelled node of arg becomes inner, its mate's node outer
+            const int v = arg, u = src;
+            const int tn = f.top[v];
+            const int m = f.mate[f.base[tn]];
+            if (m < 0) return 3;
+            const int sn = f.top[m];
+            if (lane == 0) {
+                const i16 r = f.troot[f.top[u]];
+                f.label[tn] = L_T; f.pu[tn] = (i16)u; f.pv[tn] = (i16)v; f.label[sn] = L_S;
+                f.troot[tn] = r; f.troot[sn] = r;
+                if (tn >= cap) f.yb[tn - cap] += 2 * D;   // z = zb - 2D from now on
+                if (sn >= cap) f.yb[sn - cap] -= 2 * D;   // z = zb + 2D
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (lane + 32 * k < n) {
+                    if (vtop[k] == tn) {
+                        vlab[k] = L_T; yb[k] += D;
+                        if (tm[k] < SL_INF) tm[k] -= D;
+                    } else if (vtop[k] == sn) {
+                        vlab[k] = L_S; yb[k] -= D; news[k] = true;
+                        if (tm[k] < SL_INF) tm[k] = (tm[k] + D) >> 1;
+                    }
+                }
+            }
+        } else if (type == 1) {
+            const int v = arg, u = src;
+            const int tu = f.top[u], tv = f.top[v];
+            const int r1 = f.troot[tu], r2 = f.troot[tv];
+            if (r1 == r2) {
+                GQ_STAT(3);
+                // ---- shrink the odd cycle inside one tree
+                for (int x = lane; x < nn; x += 32) f.mark[x] = 0;
+                __syncwarp();
+                int b = 0;
+                if (lane == 0) {
+                    b = shrink(f, u, v);
+                    if (b >= 0) {
+                        // children that are blossoms freeze their dual at its current value
+                        int c = f.first[b - cap];
+                        const int c0 = c;
+                        do {
+                            if (c >= cap) f.yb[c - cap] += f.label[c] == L_S ? 2 * D : -2 * D;
+                            c = f.nxt[c];
+                        } while (c != c0);
+                        f.yb[b - cap] = -2 * D;   // z = zb + 2D = 0 now
+                        f.troot[b] = (i16)r1;
+                    }
+                }
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b < 0) return 2;
+                bhi = max(bhi, b - cap + 1);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int x = lane + 32 * k;
+                    if (x < n && f.par[vtop[k]] == b) {
+                        if (vlab[k] == L_T) {
+                            news[k] = true;
+                            yb[k] -= 2 * D;
+                            if (tm[k] < SL_INF) tm[k] = D + (tm[k] >> 1);
+                        }
+                        vtop[k] = b; vlab[k] = L_S;
+                        f.top[x] = (i16)b;
+                    }
+                }
+                __syncwarp();
+            } else {
+                GQ_STAT(4);
+                // ---- augment between two trees, then dissolve exactly those two trees
+                if (lane == 0) { augment_half(f, u, v); augment_half(f, v, u); }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int x = lane + 32 * k;
+                    if (x < n && vlab[k] != L_NONE) {
+                        const int r = f.troot[vtop[k]];
+                        if (r == r1 || r == r2) {
+                            if (vlab[k] == L_S) { yb[k] += D; if (tm[k] < SL_INF) tm[k] = 2 * tm[k] - D; }
+                            else { yb[k] -= D; if (tm[k] < SL_INF) tm[k] += D; }
+                            vlab[k] = L_NONE;
+                        }
+                    }
+                    if (x == r1 || x == r2) freebits &= ~(1u << k);
+                }
+                __syncwarp();
+                for (int x = lane; x < nn; x += 32) {
+                    if (f.par[x] < 0 && f.label[x] != L_NONE && (f.troot[x] == r1 || f.troot[x] == r2)) {
+                        if (x >= cap) f.yb[x - cap] += f.label[x] == L_S ? 2 * D : -2 * D;
+                        f.label[x] = L_NONE;
+                    }
+                }
+                __syncwarp();
+                nfree -= 2;
+                if (nfree <= 0) return 0;
+            }
+        } else {
+            GQ_STAT(5);
+            // ---- expand an inner blossom whose dual reached zero
+            const int b = cap + arg;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int x = lane + 32 * k;
+                if (x < n && vtop[k] == b) {
+                    int c = x;
+                    while (f.par[c] != b) c = f.par[c];
+                    vtop[k] = c;
+                    f.top[x] = (i16)c;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const int fst = f.first[b - cap];
+                const i16 r = f.troot[b];
+                expand_relabel(f, b);
+                int c = fst;
+                do {
+                    if (f.label[c] != L_NONE) {
+                        f.troot[c] = r;
+                        if (c >= cap) f.yb[c - cap] += f.label[c] == L_S ? -2 * D : 2 * D;
+                    }
+                    c = f.nxt[c];
+                } while (c != fst);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int x = lane + 32 * k;
+                if (x < n && vlab[k] == L_T) {
+                    const int nl = f.label[vtop[k]];
+                    if (nl == L_S) {
+                        news[k] = true; yb[k] -= 2 * D;
+                        if (tm[k] < SL_INF) tm[k] = D + (tm[k] >> 1);
+                    } else if (nl == L_NONE) {
+                        yb[k] -= D;
+                        if (tm[k] < SL_INF) tm[k] += D;
+                    }
+                    vlab[k] = nl;
+                }
+            }
+        }
+        GQM_SCAN_WHERE(news);
+    }
+#undef GQM_YACT
+#undef GQM_SEL
+#undef GQM_YOF
+#undef GQM_SCAN
+#undef GQM_SCAN_WHERE
 }
 
 }  // namespace gqr

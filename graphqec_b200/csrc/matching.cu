@@ -20,6 +20,9 @@
 #include <queue>
 #include <thread>
 
+#ifdef GQ_STATS
+__device__ unsigned long long gq_stats[16];
+#endif
 #include "blossom_regs.cuh"
 #include "blossom_warp.cuh"
 #include "gq_common.h"
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(256) match_kernel(MatchArgs a) {
 // ---- fast tier: register-resident solver (blossom_regs.cuh), forest in shared memory, W in an
 // L2-resident scratch; handles shots with fewer than 32*K defects, the rest go to the overflow list
 template <int K>
-__global__ void __launch_bounds__(256, 4) match_fast_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(256, (K <= 4 ? 4 : 2)) match_fast_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     constexpr int CAP = 32 * K;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(256, 4) match_fast_kernel(MatchArgs a) {
     const uint8_t *bobs = a.pobs + (size_t)a.D * N;
 
     for (uint64_t item = warp; item < a.nitems; item += nwarps) {
-        const uint64_t shot = item;
+        const uint64_t shot = a.list ? a.list[item] : item;
         const uint32_t *row = a.dets + shot * a.DW;
         int n0 = 0;
         for (uint32_t w0 = 0; w0 < a.DW; w0 += 32) {
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(256, 4) match_fast_kernel(MatchArgs a) {
         }
         __syncwarp();
         if (n0 > CAP - 1) {
-            if (lane == 0) {
+            if (lane == 0 && a.overflow) {
                 uint32_t idx = atomicAdd(&a.overflow[0], 1u);
                 atomicMax(&a.overflow[1], (uint32_t)n0);
                 if (idx < a.overflow_cap) a.overflow[2 + idx] = (uint32_t)shot;
@@ -275,7 +278,11 @@ __global__ void __launch_bounds__(256, 4) match_fast_kernel(MatchArgs a) {
                 for (int k = 0; k < K; ++k) if (lane + 32 * k == n0) ymin[k] = mb;
             }
             __syncwarp();
+            #ifndef GQ_MULTI_TREE
             rc = gqr::solve<K>(F, Wm, stride, n, lane, ymin);
+#else
+            rc = gqr::solve_mt<K>(F, Wm, stride, n, lane, ymin);
+#endif
             __syncwarp();
             if (rc == 0) {
                 uint32_t *corr_row = a.corr_out ? a.corr_out + shot * a.EW : nullptr;
@@ -473,17 +480,31 @@ int gq_matching_create(gq_dec *dec) {
         GQ_CUDA(cudaMalloc((void **)&dec->d_adj_edge, std::max<size_t>(adj_edge.size(), 1) * 4));
         GQ_CUDA(cudaMemcpy(dec->d_adj_edge, adj_edge.data(), adj_edge.size() * 4, cudaMemcpyHostToDevice));
     }
-    // ---- fast tier: register-resident solver, K = 4 slots per lane (< 128 defects), 3 blocks of
-    // 8 warps per SM; its only global workspace is the dense weight matrix of each warp
-    dec->fast_cap = 128;
-    dec->nwarps_fast = dem->num_sms * 4 * 8;
-    dec->ws_fast_bytes = ((size_t)128 * 129 * 2 + 255) & ~(size_t)255;
-    GQ_CUDA(cudaMalloc(&dec->d_ws_fast, dec->ws_fast_bytes * dec->nwarps_fast));
+    // ---- tiers: register-resident solver with K = 1, 2, 4, 8 slots per lane (< 32K defects); the
+    // first pass uses the smallest tier that holds mu + 4 sigma defects, stragglers climb the ladder
+    // through overflow lists and anything beyond 255 defects falls to the memory-resident solver
+    {
+        double want = mu + 2.5 * sqrt(2 * mu + 1);
+        if (dec->params.fast_capacity > 0) want = dec->params.fast_capacity;
+        int k0 = 1;
+        while (k0 < 8 && 32 * k0 - 1 < want) k0 *= 2;
+        dec->fast_cap = 32u * k0;
+    }
+    GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     dec->overflow_cap = 1u << 20;
-    GQ_CUDA(cudaMalloc((void **)&dec->d_overflow, (2 + (size_t)dec->overflow_cap) * 4));
+    GQ_CUDA(cudaMalloc((void **)&dec->d_overflow, 2 * (2 + (size_t)dec->overflow_cap) * 4));
     return GQ_OK;
 }
+
+#ifdef GQ_STATS
+extern "C" void gq_debug_stats(unsigned long long *out, int reset) {
+    cudaMemcpyFromSymbol(out, gq_stats, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(gq_stats, z, sizeof(z)); }
+}
+#endif
 
 void gq_matching_destroy(gq_dec *dec) {
     cudaFree(dec->d_dist); cudaFree(dec->d_pobs); cudaFree(dec->d_next);
@@ -502,11 +523,11 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
     a.D = dem->D; a.DW = dem->DW; a.OW = dem->OW; a.EW = (dec->num_edges + 31) / 32;
     a.dist = dec->d_dist; a.pobs = dec->d_pobs; a.next = dec->d_next;
     a.adj_ptr = dec->d_adj_ptr; a.adj_node = dec->d_adj_node; a.adj_edge = dec->d_adj_edge;
-    // the overflow list is bounded: process in slices so it can never overrun
-    const uint64_t slice = 1ull << 22;
+    // the overflow lists are bounded: process in slices so they can never overrun
+    const uint64_t slice = 1ull << 20;
+    uint32_t *ovf_buf[2] = {dec->d_overflow, dec->d_overflow + 2 + dec->overflow_cap};
     for (uint64_t s0 = 0; s0 < nshots; s0 += slice) {
         uint64_t ns = std::min(slice, nshots - s0);
-        GQ_CUDA(cudaMemsetAsync(dec->d_overflow, 0, 8, dem->stream));
         MatchArgs b = a;
         b.dets = dets_sm + s0 * dem->DW;
         b.pred = pred_sm + s0 * dem->OW;
@@ -514,39 +535,64 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
         if (flags_out) b.flags_out = flags_out + s0;
         if (corr_out) b.corr_out = corr_out + s0 * a.EW;
         b.list = nullptr; b.nitems = ns;
-        b.cap = dec->fast_cap;
-        b.ws = (char *)dec->d_ws_fast; b.ws_stride = dec->ws_fast_bytes;
-        b.overflow = dec->d_overflow; b.overflow_cap = dec->overflow_cap;
-        int blocks = (int)std::min<uint64_t>((ns + 7) / 8, (uint64_t)dec->nwarps_fast / 8);
-        size_t smem = 8 * (gqr::forest_bytes(128) + 128 * 4);
-        match_fast_kernel<4><<<blocks, 256, smem, dem->stream>>>(b);
-        GQ_CUDA(cudaGetLastError());
-        ++*launches;
-        uint32_t ovf[2];
-        GQ_CUDA(cudaMemcpyAsync(ovf, dec->d_overflow, 8, cudaMemcpyDeviceToHost, dem->stream));
-        GQ_CUDA(cudaStreamSynchronize(dem->stream));
-        if (ovf[0] == 0) continue;
-        if (ovf[0] > dec->overflow_cap) GQ_FAIL(GQ_E_INTERNAL, "matching decoder: overflow list overrun; raise fast_capacity");
-        int cap = std::min<int>(even_up((int)ovf[1] + 1), (int)dec->max_cap);
-        size_t wsb = warp_ws_bytes(cap);
-        int nw = (int)std::min<uint64_t>(ovf[0], (uint64_t)dem->num_sms * 8);
-        size_t budget = (size_t)8 << 30;
-        nw = (int)std::max<size_t>(1, std::min<size_t>(nw, budget / wsb));
-        nw = std::max(8, (nw / 8) * 8);
-        if (wsb * nw > dec->ws_big_bytes) {
-            cudaFree(dec->d_ws_big);
-            dec->d_ws_big = nullptr; dec->ws_big_bytes = 0;
-            GQ_CUDA(cudaMalloc(&dec->d_ws_big, wsb * nw));
-            dec->ws_big_bytes = wsb * nw;
+        int K = (int)dec->fast_cap / 32;
+        int cur = 0;
+        for (;;) {
+            // ---- one pass of tier K over the current item list
+            const int cap = 32 * K;
+            const int per_sm = K <= 4 ? 4 : 2;
+            const int nwarps = dem->num_sms * per_sm * 8;
+            const size_t wbytes = ((size_t)cap * (cap + 1) * 2 + 255) & ~(size_t)255;
+            if (wbytes * nwarps > dec->ws_fast_bytes) {
+                cudaFree(dec->d_ws_fast);
+                dec->d_ws_fast = nullptr; dec->ws_fast_bytes = 0;
+                GQ_CUDA(cudaMalloc(&dec->d_ws_fast, wbytes * nwarps));
+                dec->ws_fast_bytes = wbytes * nwarps;
+            }
+            GQ_CUDA(cudaMemsetAsync(ovf_buf[cur], 0, 8, dem->stream));
+            b.cap = (uint32_t)cap;
+            b.ws = (char *)dec->d_ws_fast; b.ws_stride = wbytes;
+            b.overflow = ovf_buf[cur]; b.overflow_cap = dec->overflow_cap;
+            int blocks = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)nwarps / 8);
+            size_t smem = 8 * (gqr::forest_bytes(cap) + (size_t)cap * 4);
+            if (K == 1) match_fast_kernel<1><<<blocks, 256, smem, dem->stream>>>(b);
+            else if (K == 2) match_fast_kernel<2><<<blocks, 256, smem, dem->stream>>>(b);
+            else if (K == 4) match_fast_kernel<4><<<blocks, 256, smem, dem->stream>>>(b);
+            else match_fast_kernel<8><<<blocks, 256, smem, dem->stream>>>(b);
+            GQ_CUDA(cudaGetLastError());
+            ++*launches;
+            uint32_t ovf[2];
+            GQ_CUDA(cudaMemcpyAsync(ovf, ovf_buf[cur], 8, cudaMemcpyDeviceToHost, dem->stream));
+            GQ_CUDA(cudaStreamSynchronize(dem->stream));
+            if (ovf[0] == 0) break;
+            if (ovf[0] > dec->overflow_cap) GQ_FAIL(GQ_E_INTERNAL, "matching decoder: overflow list overrun");
+            b.list = ovf_buf[cur] + 2; b.nitems = ovf[0];
+            cur ^= 1;
+            int nextK = K;
+            while (nextK < 8 && 32 * nextK - 1 < (int)ovf[1]) nextK *= 2;
+            if (32 * nextK - 1 >= (int)ovf[1] && nextK != K) { K = nextK; continue; }
+            // ---- beyond the largest register tier: memory-resident solver, workspace sized by the worst shot
+            int bigcap = std::min<int>(even_up((int)ovf[1] + 1), (int)dec->max_cap);
+            size_t wsb = warp_ws_bytes(bigcap);
+            int nw = (int)std::min<uint64_t>(ovf[0], (uint64_t)dem->num_sms * 8);
+            size_t budget = (size_t)8 << 30;
+            nw = (int)std::max<size_t>(1, std::min<size_t>(nw, budget / wsb));
+            nw = std::max(8, (nw / 8) * 8);
+            if (wsb * nw > dec->ws_big_bytes) {
+                cudaFree(dec->d_ws_big);
+                dec->d_ws_big = nullptr; dec->ws_big_bytes = 0;
+                GQ_CUDA(cudaMalloc(&dec->d_ws_big, wsb * nw));
+                dec->ws_big_bytes = wsb * nw;
+            }
+            MatchArgs c = b;
+            c.cap = (uint32_t)bigcap;
+            c.ws = (char *)dec->d_ws_big; c.ws_stride = wsb;
+            c.overflow = nullptr; c.overflow_cap = 0;
+            match_kernel<<<nw / 8, 256, 0, dem->stream>>>(c);
+            GQ_CUDA(cudaGetLastError());
+            ++*launches;
+            break;
         }
-        MatchArgs c = b;
-        c.list = dec->d_overflow + 2; c.nitems = ovf[0];
-        c.cap = (uint32_t)cap;
-        c.ws = (char *)dec->d_ws_big; c.ws_stride = wsb;
-        c.overflow = nullptr; c.overflow_cap = 0;
-        match_kernel<<<nw / 8, 256, 0, dem->stream>>>(c);
-        GQ_CUDA(cudaGetLastError());
-        ++*launches;
     }
     return GQ_OK;
 }

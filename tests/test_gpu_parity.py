@@ -58,6 +58,9 @@ CASES = {
     "rot11": ("RotatedSurfaceCode", 0.005, {"distance": 11}),
     "unrot5": ("UnrotatedSurfaceCode", 0.005, {"distance": 5}),
     "rot4_even": ("RotatedSurfaceCode", 0.005, {"distance": 4}),
+    "rot9_hi": ("RotatedSurfaceCode", 0.012, {"distance": 9}),        # ~110 defects: K=4 tier, K=8 stragglers
+    "rot11_hi": ("RotatedSurfaceCode", 0.01, {"distance": 11}),       # ~157 defects: K=8 tier
+    "unrot7": ("UnrotatedSurfaceCode", 0.008, {"distance": 7}),      # > 255 defects for some shots: memory tier
     "steane": ("steane", 0.003, {}),
     "toric4": ("toric", 0.004, {"L": 4}),
 }
@@ -174,7 +177,8 @@ def test_detector_rates_match_dem_marginals():
 
 # ------------------------------------------------------------------------------------------ K3a
 @pytest.mark.parametrize("name,nshots", [("rep3", 3000), ("rep7", 3000), ("rot3", 3000), ("rot5", 3000), ("rot7", 2000),
-                                         ("rot11", 1500), ("unrot5", 1500), ("rot4_even", 2000), ("steane", 3000), ("toric4", 1500)])
+                                         ("rot11", 1500), ("unrot5", 1500), ("rot4_even", 2000), ("steane", 3000), ("toric4", 1500),
+                                         ("rot9_hi", 1000), ("rot11_hi", 800), ("unrot7", 600)])
 def test_matching_is_optimal_and_corrections_reproduce_syndrome(name, nshots):
     dem, demh, dech = case(name)
     orc, (u, v, w, om, pr) = oracle_for(dem, dech)
