@@ -6,6 +6,31 @@
 
 #include "gq_common.h"
 
+// sinter's b8 rows (ceil(D/8) bytes, unpadded) -> 4-byte aligned "sm" rows; one thread per output word
+__global__ void b8_to_sm_kernel(const uint8_t *src, uint32_t row_bytes, uint32_t DW, uint64_t nshots, uint32_t *dst) {
+    const uint64_t total = nshots * DW;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = i / DW;
+        const uint32_t w = (uint32_t)(i - s * DW);
+        const uint8_t *r = src + s * row_bytes + (size_t)w * 4;
+        const uint32_t left = row_bytes - w * 4;
+        uint32_t v = r[0];
+        if (left > 1) v |= (uint32_t)r[1] << 8;
+        if (left > 2) v |= (uint32_t)r[2] << 16;
+        if (left > 3) v |= (uint32_t)r[3] << 24;
+        dst[i] = v;
+    }
+}
+
+__global__ void sm_to_b8_kernel(const uint32_t *src, uint32_t OW, uint32_t row_bytes, uint64_t nshots, uint8_t *dst) {
+    const uint64_t total = nshots * row_bytes;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = i / row_bytes;
+        const uint32_t b = (uint32_t)(i - s * row_bytes);
+        dst[i] = (uint8_t)(src[s * OW + (b >> 2)] >> (8 * (b & 3)));
+    }
+}
+
 static void default_params(gq_decoder_params *p) {
     memset(p, 0, sizeof(*p));
     p->weight_levels = 1000;
@@ -115,19 +140,29 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
     int launches = 0;
     int rc = ensure_scratch(dec, std::min(chunk, nshots));
     if (rc) return rc;
+    if (dec->b8_bytes < chunk * (db + ob)) {
+        cudaFree(dec->d_b8);
+        dec->d_b8 = nullptr; dec->b8_bytes = 0;
+        GQ_CUDA(cudaMalloc((void **)&dec->d_b8, chunk * (db + ob)));
+        dec->b8_bytes = chunk * (db + ob);
+    }
+    uint8_t *d_in = dec->d_b8, *d_out = dec->d_b8 + chunk * db;
     for (uint64_t s0 = 0; s0 < nshots; s0 += chunk) {
         uint64_t ns = std::min(chunk, nshots - s0);
         GQ_CUDA(cudaEventRecord(e0, dem->stream));
-        // b8 rows -> 4-byte aligned rows (same bit order, zero padded)
-        GQ_CUDA(cudaMemsetAsync(dec->d_dets, 0, ns * dem->DW * 4, dem->stream));
-        GQ_CUDA(cudaMemcpy2DAsync(dec->d_dets, (size_t)dem->DW * 4, dets_b8 + s0 * db, db, db, ns,
-                                  cudaMemcpyHostToDevice, dem->stream));
+        // one contiguous copy of the b8 rows, re-strided to 4-byte aligned rows on the device
+        GQ_CUDA(cudaMemcpyAsync(d_in, dets_b8 + s0 * db, ns * db, cudaMemcpyHostToDevice, dem->stream));
+        b8_to_sm_kernel<<<dem->num_sms * 8, 256, 0, dem->stream>>>(d_in, (uint32_t)db, dem->DW, ns, dec->d_dets);
+        GQ_CUDA(cudaGetLastError());
+        ++launches;
         GQ_CUDA(cudaEventRecord(e1, dem->stream));
         rc = decode_dispatch(dec, dec->d_dets, ns, dec->d_pred, nullptr, nullptr, nullptr, &launches);
         if (rc) return rc;
         GQ_CUDA(cudaEventRecord(e2, dem->stream));
-        GQ_CUDA(cudaMemcpy2DAsync(pred_b8 + s0 * ob, ob, dec->d_pred, (size_t)dem->OW * 4, ob, ns,
-                                  cudaMemcpyDeviceToHost, dem->stream));
+        sm_to_b8_kernel<<<dem->num_sms * 2, 256, 0, dem->stream>>>(dec->d_pred, dem->OW, (uint32_t)ob, ns, d_out);
+        GQ_CUDA(cudaGetLastError());
+        ++launches;
+        GQ_CUDA(cudaMemcpyAsync(pred_b8 + s0 * ob, d_out, ns * ob, cudaMemcpyDeviceToHost, dem->stream));
         GQ_CUDA(cudaEventRecord(e3, dem->stream));
         GQ_CUDA(cudaStreamSynchronize(dem->stream));
         float ms;
