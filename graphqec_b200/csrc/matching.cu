@@ -27,6 +27,10 @@ __device__ unsigned long long gq_stats[16];
 #include "blossom_warp.cuh"
 #include "gq_common.h"
 
+#ifndef GQ_PER_SM
+#define GQ_PER_SM 4
+#endif
+
 struct MatchArgs {
     const uint32_t *dets;
     uint32_t *pred;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(256) match_kernel(MatchArgs a) {
 // ---- fast tier: register-resident solver (blossom_regs.cuh), forest in shared memory, W in an
 // L2-resident scratch; handles shots with fewer than 32*K defects, the rest go to the overflow list
 template <int K>
-__global__ void __launch_bounds__(256, (K <= 4 ? 4 : 2)) match_fast_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     constexpr int CAP = 32 * K;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(256, (K <= 4 ? 4 : 2)) match_fast_kernel(Match
                 for (int k = 0; k < K; ++k) if (lane + 32 * k == n0) ymin[k] = mb;
             }
             __syncwarp();
-            #ifndef GQ_MULTI_TREE
+            #if !defined(GQ_MULTI_TREE)
             rc = gqr::solve<K>(F, Wm, stride, n, lane, ymin);
 #else
             rc = gqr::solve_mt<K>(F, Wm, stride, n, lane, ymin);
@@ -286,10 +290,13 @@ __global__ void __launch_bounds__(256, (K <= 4 ? 4 : 2)) match_fast_kernel(Match
             __syncwarp();
             if (rc == 0) {
                 uint32_t *corr_row = a.corr_out ? a.corr_out + shot * a.EW : nullptr;
+                int bad = 0;
                 for (int i = lane; i < n0; i += 32) {
                     int j = F.mate[i];
                     const uint32_t di = def[i];
+                    if (j < 0) { bad = 1; continue; }
                     if (j == n0) {
+                        if (bd[i] == 0xFFFFu) bad = 1;
                         pm ^= bobs[di];
                         wt += bd[i];
                         if (corr_row) walk_path(a, di, a.D, corr_row);
@@ -297,6 +304,7 @@ __global__ void __launch_bounds__(256, (K <= 4 ? 4 : 2)) match_fast_kernel(Match
                         const uint32_t dj2 = def[j];
                         uint32_t d = a.dist[(size_t)dj2 * N + di];
                         uint32_t s = (bd[i] == 0xFFFFu || bd[j] == 0xFFFFu) ? 0xFFFFu : (uint32_t)bd[i] + bd[j];
+                        if (min(d, s) >= 0xFFFFu) bad = 1;   // matched through a missing edge: no perfect matching
                         if (d <= s) {
                             pm ^= a.pobs[(size_t)dj2 * N + di];
                             wt += (int)d;
@@ -310,6 +318,7 @@ __global__ void __launch_bounds__(256, (K <= 4 ? 4 : 2)) match_fast_kernel(Match
                 }
                 pm = __reduce_xor_sync(0xffffffffu, pm);
                 wt = __reduce_add_sync(0xffffffffu, wt);
+                if (__any_sync(0xffffffffu, bad)) rc = 1;
             }
         }
         if (lane == 0) {
@@ -540,7 +549,7 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
         for (;;) {
             // ---- one pass of tier K over the current item list
             const int cap = 32 * K;
-            const int per_sm = K <= 4 ? 4 : 2;
+            const int per_sm = K <= 4 ? GQ_PER_SM : 2;
             const int nwarps = dem->num_sms * per_sm * 8;
             const size_t wbytes = ((size_t)cap * (cap + 1) * 2 + 255) & ~(size_t)255;
             if (wbytes * nwarps > dec->ws_fast_bytes) {

@@ -13,7 +13,7 @@ lib.gq_debug_stats(out, 1)
 n = 1 << 18
 res = d.collect(1, 0, n, 0)
 lib.gq_debug_stats(out, 1)
-names = ["events(search)", "stale pops", "grow", "shrink", "augment", "expand", "scans", "shots", "free after greedy"]
+names = ["events(search)", "stale pops", "grow", "shrink", "augment", "expand", "scans", "shots", "free after greedy", "eager recomputes"]
 print(libpath, res, d.last_timing()["decode_ms"])
 shots = out[7]
 for k, nm in enumerate(names): print("  %-20s %.2f per shot" % (nm, out[k] / max(1, shots)))
