@@ -123,7 +123,8 @@ __device__ __forceinline__ void augment(const Forest &f, int u, int v) {
         int x = f.top[a];
         int m = f.mate[f.base[x]];
         rebase(f, x, a);
-        f.mate[a] = (i16)nm; f.mate[nm] = (i16)a;
+        f.mate[a] = (i16)nm;
+        if (nm >= 0) f.mate[nm] = (i16)a;
         if (m < 0) break;
         int t = f.top[m];
         int tpu = f.pu[t], tpv = f.pv[t];
@@ -444,6 +445,289 @@ __device__ __forceinline__ int solve(const Forest &f, const u16 *W, const int ws
                     if (vtop[k] == t) vlab[k] = L_T;
                     else if (vtop[k] == s && lane + 32 * k < n) { vlab[k] = L_S; news[k] = true; }
                 }
+            } else if (type == 1) {
+                const int v = arg, u = src;
+                for (int x = lane; x < nn; x += 32) f.mark[x] = 0;
+                __syncwarp();
+                int b = 0;
+                GQ_STAT(3);
+                if (lane == 0) b = shrink(f, u, v);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b < 0) return 2;
+                bhi = max(bhi, b - cap + 1);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    news[k] = false;
+                    const int x = lane + 32 * k;
+                    if (x < n && f.par[vtop[k]] == b) {
+                        news[k] = vlab[k] == L_T;   // inner vertices turn outer: they must be offered
+                        vtop[k] = b; vlab[k] = L_S;
+                        f.top[x] = (i16)b;
+                    }
+                }
+                __syncwarp();
+            } else {
+                GQ_STAT(5);
+                const int b = cap + arg;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int x = lane + 32 * k;
+                    if (x < n && vtop[k] == b) {
+                        int c = x;
+                        while (f.par[c] != b) c = f.par[c];
+                        vtop[k] = c;
+                        f.top[x] = (i16)c;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) expand_relabel(f, b);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int x = lane + 32 * k;
+                    news[k] = false;
+                    if (x < n) {
+                        int nl = f.label[vtop[k]];
+                        news[k] = nl == L_S && vlab[k] != L_S;
+                        vlab[k] = nl;
+                    }
+                }
+            }
+            GQR_SCAN_WHERE(news);
+        }
+    }
+    return 0;
+#undef GQR_SEL
+#undef GQR_SCAN
+#undef GQR_SCAN_WHERE
+}
+
+// ---------------------------------------------------------------- native-boundary variant (default)
+// The boundary is a special always-free partner: vertex v may be matched to it at cost b(v)
+// (mate = -2).  W holds true distances d(i,j) only, there is no virtual vertex and n may be odd.
+// An outer vertex whose boundary slack 2b - y reaches zero ends the phase (event type 3); reaching
+// a vertex that is matched to the boundary also ends it (its boundary edge is an augmenting step).
+// Compared with the min(d, b_i+b_j) form this halves the free vertices left after the greedy start
+// (11 instead of 22 per shot at the north star) and keeps trees short near the boundary.
+// yinit[k] = minimum weight incident to vertex lane + 32k (undoubled); n even; W row stride wstride.
+// Returns 0 ok, 1 no perfect matching, 2 blossom ids exhausted, 3 step guard.  mate[] ends in f.mate.
+template <int K>
+__device__ __forceinline__ int solve_nb(const Forest &f, const u16 *W, const int wstride, const int n,
+                                        const int lane, const uint32_t (&yinit)[K], const uint32_t (&bnd)[K]) {
+    const int cap = f.cap, nb = f.nb, nn = cap + nb;
+    const int kmax = (n + 31) >> 5;   // slots in use (uniform)
+    int bhi = 0;                      // blossom ids in use are below cap + bhi
+    i32 y[K], sl[K], b2[K];   // b2 = doubled boundary distance (SL_INF: none)
+    int slfrom[K], vtop[K], vlab[K];
+
+#define GQR_SEL(arr, u, out)                                           \
+    {                                                                  \
+        int sel_ = arr[0];                                             \
+        _Pragma("unroll") for (int k_ = 1; k_ < K; ++k_) if (((u) >> 5) == k_) sel_ = arr[k_]; \
+        out = __shfl_sync(0xffffffffu, sel_, (u) & 31);                \
+    }
+#define GQR_SCAN(u_)                                                   \
+    {                                                                  \
+        const int su_ = (u_);                                          \
+        const int tu_ = f.top[su_];                                    \
+        i32 yu_;                                                       \
+        GQR_SEL(y, su_, yu_);                                          \
+        const u16 *row_ = W + su_ * wstride;                           \
+        _Pragma("unroll") for (int k_ = 0; k_ < K; ++k_) {             \
+            const int v_ = lane + 32 * k_;                             \
+            if (k_ < kmax && v_ < n && vtop[k_] != tu_) {              \
+                u16 wt_ = row_[v_];                                    \
+                if (wt_ != W_INF) {                                    \
+                    i32 s_ = 2 * (i32)wt_ - yu_ - y[k_];               \
+                    if (s_ < sl[k_]) { sl[k_] = s_; slfrom[k_] = su_; } \
+                }                                                      \
+            }                                                          \
+        }                                                              \
+    }
+#define GQR_SCAN_WHERE(pred)                                           \
+    {                                                                  \
+        _Pragma("unroll") for (int kk_ = 0; kk_ < K; ++kk_) {          \
+            unsigned m_ = kk_ < kmax ? __ballot_sync(0xffffffffu, pred[kk_]) : 0u; \
+            while (m_) {                                               \
+                int b_ = __ffs(m_) - 1;                                \
+                m_ &= m_ - 1;                                          \
+                GQ_STAT(6); GQR_SCAN(32 * kk_ + b_);                   \
+            }                                                          \
+        }                                                              \
+    }
+
+    for (int x = lane; x < nn; x += 32) { f.base[x] = (i16)(x < cap ? x : -1); f.par[x] = -1; f.label[x] = L_NONE; f.mark[x] = 0; }
+    for (int i = lane; i < nb; i += 32) f.bused[i] = 0;
+    unsigned freebits = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int v = lane + 32 * k;
+        vtop[k] = v; vlab[k] = L_NONE; sl[k] = SL_INF; slfrom[k] = -1;
+        b2[k] = bnd[k] == (uint32_t)W_INF ? SL_INF : 2 * (i32)bnd[k];
+        y[k] = yinit[k] == (uint32_t)W_INF ? 0 : (i32)yinit[k];
+        if (y[k] > b2[k] || yinit[k] == (uint32_t)W_INF) y[k] = b2[k] == SL_INF ? 0 : b2[k];
+        if (v < n) {
+            f.top[v] = (i16)v;
+            if (y[k] == b2[k]) f.mate[v] = -2;            // tight boundary edge: start matched to it
+            else { f.mate[v] = -1; freebits |= 1u << k; }
+        }
+    }
+    __syncwarp();
+    // ---- greedy matching along tight edges
+    for (int u = 0; u < n; ++u) {
+        unsigned ufree = (__shfl_sync(0xffffffffu, freebits, u & 31) >> (u >> 5)) & 1u;
+        if (!ufree) continue;
+        i32 yu;
+        GQR_SEL(y, u, yu);
+        const u16 *row = W + u * wstride;
+        int found = -1;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int v = lane + 32 * k;
+            bool ok = false;
+            if (k < kmax && found < 0 && v < n && v != u && ((freebits >> k) & 1u)) {
+                u16 wt = row[v];
+                ok = wt != W_INF && 2 * (i32)wt - yu - y[k] == 0;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (found < 0 && m) found = 32 * k + __ffs(m) - 1;
+        }
+        if (found >= 0) {
+            if (lane == 0) { f.mate[u] = (i16)found; f.mate[found] = (i16)u; }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int v = lane + 32 * k;
+                if (v == u || v == found) freebits &= ~(1u << k);
+            }
+        }
+    }
+    __syncwarp();
+    GQ_STAT(7);
+#ifdef GQ_STATS
+    { int nf_ = __reduce_add_sync(0xffffffffu, __popc(freebits)); if (lane == 0) atomicAdd(&gq_stats[8], (unsigned long long)nf_); }
+#endif
+    // ---- phases: one alternating tree per free vertex
+    for (int root = 0; root < n; ++root) {
+        unsigned rfree = (__shfl_sync(0xffffffffu, freebits, root & 31) >> (root >> 5)) & 1u;
+        if (!rfree) continue;
+        for (int x = lane; x < nn; x += 32) f.label[x] = L_NONE;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { vlab[k] = L_NONE; sl[k] = SL_INF; slfrom[k] = -1; }
+        __syncwarp();
+        if (lane == 0) f.label[root] = L_S;
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (lane + 32 * k == root) vlab[k] = L_S;
+        __syncwarp();
+        GQR_SCAN(root);
+        for (int guard = 0;; ++guard) {
+            if (guard > 8 * nn + 64) return 3;
+            // ---- minimum-slack event: key = delta << 10 | type << 8 | arg
+            unsigned best = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int v = lane + 32 * k;
+                if (k < kmax && v < n && sl[k] < SL_INF) {
+                    if (vlab[k] == L_NONE) best = min(best, ((unsigned)sl[k] << 10) | (unsigned)v);
+                    else if (vlab[k] == L_S) best = min(best, ((unsigned)(sl[k] >> 1) << 10) | 0x100u | (unsigned)v);
+                }
+                if (k < kmax && v < n && vlab[k] == L_S && b2[k] < SL_INF)
+                    best = min(best, ((unsigned)(b2[k] - y[k]) << 10) | 0x300u | (unsigned)v);
+            }
+            for (int i = lane; i < bhi; i += 32)
+                if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] == L_T)
+                    best = min(best, ((unsigned)(f.yb[i] >> 1) << 10) | 0x200u | (unsigned)i);
+            best = __reduce_min_sync(0xffffffffu, best);
+            GQ_STAT(0);
+            if (best == 0xffffffffu) return 1;
+            const i32 delta = (i32)(best >> 10);
+            const int type = (best >> 8) & 3;
+            const int arg = best & 0xff;
+            int src = -1;
+            if (type < 2) GQR_SEL(slfrom, arg, src);
+            if (type == 1 && f.top[src] == f.top[arg]) {
+                GQ_STAT(1);
+                // lazy validation: the source was swallowed by the same blossom -> recompute the exact
+                // slack of outer vertex arg towards outer vertices of other nodes, then search again
+                const int tv = f.top[arg];
+                i32 yv;
+                GQR_SEL(y, arg, yv);
+                const u16 *row = W + arg * wstride;
+                unsigned long long bb = ~0ull;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int u = lane + 32 * k;
+                    if (k < kmax && u < n && vlab[k] == L_S && vtop[k] != tv) {
+                        u16 wt = row[u];
+                        if (wt != W_INF) {
+                            i32 s = 2 * (i32)wt - yv - y[k];
+                            unsigned long long key = ((unsigned long long)(unsigned)s << 16) | (unsigned)u;
+                            if (key < bb) bb = key;
+                        }
+                    }
+                }
+                unsigned hi = (unsigned)(bb >> 32), lo = (unsigned)bb;
+                unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+                unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+                bb = ((unsigned long long)mh << 32) | ml;
+                const i32 ns = bb == ~0ull ? SL_INF : (i32)(bb >> 16);
+                const int nf = bb == ~0ull ? -1 : (int)(bb & 0xffff);
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (lane + 32 * k == arg) { sl[k] = ns; slfrom[k] = nf; }
+                continue;
+            }
+            // ---- dual update
+            if (delta) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (k >= kmax) continue;
+                    if (vlab[k] == L_S) { y[k] += delta; if (sl[k] < SL_INF) sl[k] -= 2 * delta; }
+                    else if (vlab[k] == L_T) y[k] -= delta;
+                    else if (sl[k] < SL_INF) sl[k] -= delta;
+                }
+                for (int i = lane; i < bhi; i += 32)
+                    if (f.bused[i] && f.par[cap + i] < 0) {
+                        if (f.label[cap + i] == L_S) f.yb[i] += 2 * delta;
+                        else if (f.label[cap + i] == L_T) f.yb[i] -= 2 * delta;
+                    }
+                __syncwarp();
+            }
+            bool news[K];
+            if (type == 0) {
+                const int v = arg, u = src;
+                const int t = f.top[v];
+                const int m = f.mate[f.base[t]];
+                if (m < 0) {
+                    GQ_STAT(4);
+                    if (lane == 0) { rebase(f, t, v); augment(f, u, v); }
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int x = lane + 32 * k;
+                        if (x == root || x == v) freebits &= ~(1u << k);
+                    }
+                    break;
+                }
+                GQ_STAT(2);
+                const int s = f.top[m];
+                if (lane == 0) { f.label[t] = L_T; f.pu[t] = (i16)u; f.pv[t] = (i16)v; f.label[s] = L_S; }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    news[k] = false;
+                    if (vtop[k] == t) vlab[k] = L_T;
+                    else if (vtop[k] == s && lane + 32 * k < n) { vlab[k] = L_S; news[k] = true; }
+                }
+            } else if (type == 3) {
+                // ---- outer vertex arg reaches the boundary: match it there, flip the path to the root
+                GQ_STAT(4);
+                if (lane == 0) augment(f, arg, -2);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (lane + 32 * k == root) freebits &= ~(1u << k);
+                break;
             } else if (type == 1) {
                 const int v = arg, u = src;
                 for (int x = lane; x < nn; x += 32) f.mark[x] = 0;

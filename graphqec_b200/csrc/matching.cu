@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
         uint32_t pm = 0;
         int wt = 0, rc = 0;
         if (n0 > 0) {
-            const int n = n0 + (n0 & 1);
+            // native-boundary form: W[i][j] = d(i, j) only, boundary distances travel separately
+            const int n = n0;
             const int stride = n + 1;
             uint32_t dj[K], bj[K], ymin[K];
 #pragma unroll
@@ -253,40 +254,20 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
             __syncwarp();
             for (int i = 0; i < n0; ++i) {
                 const uint32_t di = def[i];
-                const uint32_t bi = bd[i];
                 const uint16_t *drow = a.dist + (size_t)di * N;
                 uint16_t *wrow = Wm + i * stride;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const int j = lane + 32 * k;
                     if (j < n0) {
-                        uint32_t d = drow[dj[k]];
-                        uint32_t s = (bi == 0xFFFFu || bj[k] == 0xFFFFu) ? 0xFFFFu : min(bi + bj[k], 0xFFFEu);
-                        uint32_t w = j == i ? 0xFFFFu : min(d, s);
+                        uint32_t w = j == i ? 0xFFFFu : (uint32_t)drow[dj[k]];
                         wrow[j] = (uint16_t)w;
                         ymin[k] = min(ymin[k], w);
                     }
                 }
-                if (n != n0 && lane == 0) wrow[n0] = (uint16_t)bi;
-            }
-            if (n != n0) {
-                uint32_t mb = 0xFFFFu;
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int j = lane + 32 * k;
-                    if (j < n0) { Wm[n0 * stride + j] = (uint16_t)bj[k]; ymin[k] = min(ymin[k], bj[k]); mb = min(mb, bj[k]); }
-                }
-                mb = __reduce_min_sync(0xffffffffu, mb);
-                if (lane == 0) Wm[n0 * stride + n0] = 0xFFFFu;
-#pragma unroll
-                for (int k = 0; k < K; ++k) if (lane + 32 * k == n0) ymin[k] = mb;
             }
             __syncwarp();
-            #if !defined(GQ_MULTI_TREE)
-            rc = gqr::solve<K>(F, Wm, stride, n, lane, ymin);
-#else
-            rc = gqr::solve_mt<K>(F, Wm, stride, n, lane, ymin);
-#endif
+            rc = gqr::solve_nb<K>(F, Wm, stride, n, lane, ymin, bj);
             __syncwarp();
             if (rc == 0) {
                 uint32_t *corr_row = a.corr_out ? a.corr_out + shot * a.EW : nullptr;
@@ -294,26 +275,20 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
                 for (int i = lane; i < n0; i += 32) {
                     int j = F.mate[i];
                     const uint32_t di = def[i];
-                    if (j < 0) { bad = 1; continue; }
-                    if (j == n0) {
+                    if (j == -2) {                       // matched to the boundary
                         if (bd[i] == 0xFFFFu) bad = 1;
                         pm ^= bobs[di];
                         wt += bd[i];
                         if (corr_row) walk_path(a, di, a.D, corr_row);
+                    } else if (j < 0) {
+                        bad = 1;
                     } else if (j > i) {
                         const uint32_t dj2 = def[j];
                         uint32_t d = a.dist[(size_t)dj2 * N + di];
-                        uint32_t s = (bd[i] == 0xFFFFu || bd[j] == 0xFFFFu) ? 0xFFFFu : (uint32_t)bd[i] + bd[j];
-                        if (min(d, s) >= 0xFFFFu) bad = 1;   // matched through a missing edge: no perfect matching
-                        if (d <= s) {
-                            pm ^= a.pobs[(size_t)dj2 * N + di];
-                            wt += (int)d;
-                            if (corr_row) walk_path(a, di, dj2, corr_row);
-                        } else {
-                            pm ^= bobs[di] ^ bobs[dj2];
-                            wt += (int)s;
-                            if (corr_row) { walk_path(a, di, a.D, corr_row); walk_path(a, dj2, a.D, corr_row); }
-                        }
+                        if (d >= 0xFFFFu) bad = 1;       // matched through a missing edge: no perfect matching
+                        pm ^= a.pobs[(size_t)dj2 * N + di];
+                        wt += (int)d;
+                        if (corr_row) walk_path(a, di, dj2, corr_row);
                     }
                 }
                 pm = __reduce_xor_sync(0xffffffffu, pm);
