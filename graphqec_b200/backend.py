@@ -33,7 +33,8 @@ class _Params(ctypes.Structure):
         ("with_corrections", c_int32),
         ("bp_max_iter", c_int32),
         ("bp_alpha", c_float),
-        ("reserved", c_int32 * 8),
+        ("legacy_tiers", c_int32),
+        ("reserved", c_int32 * 7),
     ]
 
 
@@ -222,7 +223,8 @@ class DecoderHandle:
     """Device-resident decoder (``gq_dec``): exact matching or min-sum BP."""
 
     def __init__(self, demh: DemHandle, kind: int = MATCHING, weight_levels: int = 0, fast_capacity: int = 0,
-                 with_corrections: bool = False, bp_max_iter: int = 0, bp_alpha: float = 0.0) -> None:
+                 with_corrections: bool = False, bp_max_iter: int = 0, bp_alpha: float = 0.0,
+                 legacy_tiers: bool = False) -> None:
         lib = load_library()
         self.demh = demh
         self.kind = kind
@@ -231,6 +233,7 @@ class DecoderHandle:
         p.weight_levels, p.fast_capacity = int(weight_levels), int(fast_capacity)
         p.with_corrections = int(bool(with_corrections))
         p.bp_max_iter, p.bp_alpha = int(bp_max_iter), float(bp_alpha)
+        p.legacy_tiers = int(bool(legacy_tiers))
         _check(lib.gq_decoder_create(demh._h, kind, ctypes.byref(p), ctypes.byref(self._h)), "gq_decoder_create")
         gi = _GraphInfo()
         _check(lib.gq_decoder_get_graph_info(self._h, ctypes.byref(gi)), "gq_decoder_get_graph_info")

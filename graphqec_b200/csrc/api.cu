@@ -50,6 +50,7 @@ extern "C" int gq_decoder_create(gq_dem *dem, int kind, const gq_decoder_params 
         if (params->weight_levels > 0) dec->params.weight_levels = params->weight_levels;
         dec->params.fast_capacity = params->fast_capacity;
         dec->params.with_corrections = params->with_corrections;
+        dec->params.legacy_tiers = params->legacy_tiers;
         if (params->bp_max_iter > 0) dec->params.bp_max_iter = params->bp_max_iter;
         if (params->bp_alpha > 0) dec->params.bp_alpha = params->bp_alpha;
     }

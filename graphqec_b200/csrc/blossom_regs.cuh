@@ -77,8 +77,24 @@ __device__ __forceinline__ Forest forest_bind(char *p, int cap) {
     return f;
 }
 
+// Same forest with every array at a compile-time offset from one base pointer (no pointer
+// registers): the per-warp shared-memory block of the first tier (match_tree.cuh).
+template <int CAP>
+struct StaticForest {
+    static constexpr int cap = CAP, nb = CAP / 2, nn = CAP + CAP / 2;
+    i32 yb[nb];
+    i16 mate[cap], top[cap];
+    i16 base[nn], par[nn], nxt[nn], prv[nn], eu[nn], ev[nn], pu[nn], pv[nn];
+    i16 first[nb];
+    i16 stk[2 * nn];
+    int8_t label[nn], mark[nn];
+    int8_t bused[nb];
+};
+
 // ---------------------------------------------------------------- lane 0 forest surgery
-__device__ __forceinline__ void rebase(const Forest &f, int x0, int a0) {
+// (FT = Forest or StaticForest<CAP>)
+template <class FT>
+__device__ __forceinline__ void rebase(FT &f, int x0, int a0) {
     const int cap = f.cap;
     int sp = 0;
     f.stk[sp++] = (i16)x0; f.stk[sp++] = (i16)a0;
@@ -117,7 +133,8 @@ __device__ __forceinline__ void rebase(const Forest &f, int x0, int a0) {
     }
 }
 
-__device__ __forceinline__ void augment(const Forest &f, int u, int v) {
+template <class FT>
+__device__ __forceinline__ void augment(FT &f, int u, int v) {
     int a = u, nm = v;
     for (;;) {
         int x = f.top[a];
@@ -135,7 +152,8 @@ __device__ __forceinline__ void augment(const Forest &f, int u, int v) {
 
 // one side of an augmentation between two trees: flip the path from outer vertex u to its root and
 // point u at its new mate nm (the caller's other half sets mate[nm])
-__device__ __forceinline__ void augment_half(const Forest &f, int u, int nm0) {
+template <class FT>
+__device__ __forceinline__ void augment_half(FT &f, int u, int nm0) {
     int a = u, nm = nm0, first = 1;
     for (;;) {
         int x = f.top[a];
@@ -152,7 +170,8 @@ __device__ __forceinline__ void augment_half(const Forest &f, int u, int nm0) {
     }
 }
 
-__device__ __forceinline__ int parent_S(const Forest &f, int x, int *tnode) {
+template <class FT>
+__device__ __forceinline__ int parent_S(FT &f, int x, int *tnode) {
     int m = f.mate[f.base[x]];
     if (m < 0) return -1;
     int t = f.top[m];
@@ -161,7 +180,8 @@ __device__ __forceinline__ int parent_S(const Forest &f, int x, int *tnode) {
 }
 
 // mark[] must be zero on entry
-__device__ __forceinline__ int shrink(const Forest &f, int u, int v) {
+template <class FT>
+__device__ __forceinline__ int shrink(FT &f, int u, int v) {
     const int cap = f.cap, nb = f.nb;
     int xu = f.top[u], xv = f.top[v];
     for (int x = xu; x >= 0;) { f.mark[x] = 1; int t; x = parent_S(f, x, &t); }
@@ -214,7 +234,8 @@ __device__ __forceinline__ int shrink(const Forest &f, int u, int v) {
 }
 
 // relabel the children of T blossom b (top[] of its vertices already points at them)
-__device__ __forceinline__ void expand_relabel(const Forest &f, int b) {
+template <class FT>
+__device__ __forceinline__ void expand_relabel(FT &f, int b) {
     const int cap = f.cap;
     const int fst = f.first[b - cap];
     const int c = f.top[f.pv[b]];

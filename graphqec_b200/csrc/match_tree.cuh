@@ -1,0 +1,501 @@
+// K3a, first tier: one shot per warp, no materialised weight matrix.
+//
+// decode_shot<K>() takes the defect list of one shot (32*(K-1) < n <= 32*K defects, ascending
+// detector index) and returns the exact minimum-weight matching's observable prediction:
+//   1. all-pairs pass over the L2-resident distance table: nearest other defect of every defect;
+//   2. dual start y(v) = min(nearest/2, boundary distance): a vertex whose boundary is at least as
+//      close as half its nearest defect starts matched to the boundary; mutual nearest neighbours
+//      are tight and start matched to each other (one lane-parallel step, no sequential greedy);
+//   3. solve_tree<K>(): primal-dual blossom, one alternating tree per remaining free vertex, the
+//      boundary as an always-free partner.  Vertex v lives in slot (v >> 5) of lane (v & 31): dual,
+//      pending event time, label are registers; the blossom forest (lane 0 walks it) sits in shared
+//      memory at compile-time offsets; weights are gathered straight from the distance table (row
+//      of the scanning vertex, columns = this lane's defects);
+//   4. XOR of the path observables of the matched pairs.
+// Replaces PyMatching's decode_batch together with matching.cu.
+//
+// Dual bookkeeping: units are quadrupled (y_u + y_v <= 4 w, y_v <= 4 b_v; all start values even) so
+// every event time is an integer.  Inside a phase values are stored against the phase clock D, so
+// a dual step touches nothing:
+//   vertex dual   y = yb + sg*D        (sg = +1 outer "S", -1 inner "T", 0 unlabelled)
+//   blossom dual  z = zb + 2*sg*D
+//   tm            clock value at which the best known edge from an outer vertex of another node
+//                 turns tight (unlabelled target: D0 + slack, outer target: D0 + slack/2); for an
+//                 inner vertex its frozen slack.
+// The only stale entries are outer-outer ones whose source was swallowed by the target's blossom;
+// they are lower bounds and are recomputed when they win the search.
+//
+// The same source compiles for the host with one lane (GQ_HOST_SIM, tests/hostsim/) so that the
+// logic can be checked against the oracle on a CPU-only box; that build is test scaffolding.
+#pragma once
+#include <stdint.h>
+
+#include "blossom_regs.cuh"
+
+#ifdef GQ_HOST_SIM
+#define GQW_LANES 1
+#define GQW_LOG 0
+typedef unsigned __int128 gqw_mask;   // one bit per slot; the single host lane owns every slot
+#else
+#define GQW_LANES 32
+#define GQW_LOG 5
+typedef unsigned gqw_mask;
+#endif
+#define GQW_FULL 0xffffffffu
+#define GQW_BIT(k) ((gqw_mask)1 << (k))
+
+#ifdef GQ_MT_STATS
+#define GQM_STAT(i, x) do { if (lane == 0) gqm_stat_add((i), (x)); } while (0)
+#else
+#define GQM_STAT(i, x) do { } while (0)
+#endif
+
+namespace gqt {
+
+using gqr::i16;
+using gqr::i32;
+using gqr::u16;
+using gqr::L_NONE;
+using gqr::L_S;
+using gqr::L_T;
+using gqr::SL_INF;
+using gqr::W_INF;
+
+struct Tables {
+    const u16 *dist;       // [D+1][D+1], row D = distances to the boundary, diagonal = W_INF
+    const uint8_t *pobs;   // [D+1][D+1] observable mask of the shortest path
+    uint32_t N, D;         // N = D + 1
+};
+
+// ---- defect list of one bit-packed syndrome row (ascending detector index); returns the count,
+// stores the first cap entries
+__device__ __forceinline__ int extract_defects(const uint32_t *row, uint32_t DW, uint32_t D, int lane,
+                                               u16 *def, int cap) {
+    int n0 = 0;
+    for (uint32_t w0 = 0; w0 < DW; w0 += GQW_LANES) {
+        const uint32_t wi = w0 + lane;
+        uint32_t word = wi < DW ? row[wi] : 0u;
+        if (wi == DW - 1 && (D & 31)) word &= (1u << (D & 31)) - 1;
+        const int cnt = __popc(word);
+        int pre = cnt;
+#pragma unroll
+        for (int o = 1; o < GQW_LANES; o <<= 1) {
+            int t = __shfl_up_sync(GQW_FULL, pre, o);
+            if (lane >= o) pre += t;
+        }
+        const int tot = __shfl_sync(GQW_FULL, pre, GQW_LANES - 1);
+        int pos = n0 + pre - cnt;
+        while (word) {
+            int b = __ffs(word) - 1;
+            word &= word - 1;
+            if (pos < cap) def[pos] = (u16)(wi * 32 + b);
+            ++pos;
+        }
+        n0 += tot;
+    }
+    __syncwarp();
+    return n0;
+}
+
+
+// arr[slot] for a warp-uniform slot, written as a select tree on the bits of slot: a chain of
+// "slot == k" selects gets folded back into a dynamically indexed (local-memory) array by the compiler
+template <int K, class TV>
+__device__ __forceinline__ int sel_slot(const TV (&arr)[K], const int slot) {
+    if constexpr (K == 1) return (int)arr[0];
+    else if constexpr (K == 2) return (slot & 1) ? (int)arr[1] : (int)arr[0];
+    else if constexpr (K == 3) return (slot & 2) ? (int)arr[2] : ((slot & 1) ? (int)arr[1] : (int)arr[0]);
+    else if constexpr (K == 4) {
+        const int lo = (slot & 1) ? (int)arr[1] : (int)arr[0];
+        const int hi = (slot & 1) ? (int)arr[3] : (int)arr[2];
+        return (slot & 2) ? hi : lo;
+    } else return (int)arr[slot];
+}
+
+// ---- single-tree blossom phases with native boundary.
+// In: f.mate[] initial matching (-1 free, -2 boundary, else partner; every matched edge tight),
+// yb[] feasible duals (quadrupled units, even), b4[] 4*boundary distance or SL_INF, freebits = slots
+// of this lane that are free.  Out: f.mate[].  Returns 0 ok, 1 no perfect matching, 2 blossom ids
+// exhausted, 3 step guard.
+template <int K, class FT>
+__device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, const uint32_t N,
+                                          const u16 *def, const int n, const int lane,
+                                          const uint32_t (&dj)[K], const i32 (&b4)[K], i32 (&yb)[K],
+                                          gqw_mask freebits) {
+    constexpr int cap = FT::cap;
+    i32 tm[K];
+    int slfrom[K], vtop[K], vlab[K];
+    i32 D = 0;
+    int bhi = 0;
+
+#define GQT_YACT(k_, t_) (yb[k_] + (vlab[k_] == L_S ? (t_) : (vlab[k_] == L_T ? -(t_) : 0)))
+#define GQT_SEL(arr, u, out) { out = __shfl_sync(GQW_FULL, sel_slot<K>(arr, (u) >> GQW_LOG), (u) & (GQW_LANES - 1)); }
+// scan the row of outer vertex u_ (its dual is yb + D): offer its edges to every vertex of other nodes
+#define GQT_SCAN(u_)                                                                            \
+    {                                                                                           \
+        const int su_ = (u_);                                                                   \
+        const int tu_ = f.top[su_];                                                             \
+        i32 yu_;                                                                                \
+        GQT_SEL(yb, su_, yu_);                                                                  \
+        yu_ += D;                                                                               \
+        const uint32_t ro_ = (uint32_t)def[su_] * N;                                            \
+        _Pragma("unroll") for (int k_ = 0; k_ < K; ++k_) {                                      \
+            const u16 wt_ = dist[ro_ + dj[k_]];                                                 \
+            if (lane + GQW_LANES * k_ < n && vtop[k_] != tu_ && wt_ != W_INF) {                 \
+                const i32 s_ = 4 * (i32)wt_ - yu_ - GQT_YACT(k_, D);                            \
+                const i32 c_ = vlab[k_] == L_NONE ? D + s_ : (vlab[k_] == L_S ? D + (s_ >> 1) : s_); \
+                if (c_ < tm[k_]) { tm[k_] = c_; slfrom[k_] = su_; }                             \
+            }                                                                                   \
+        }                                                                                       \
+    }
+#define GQT_SCAN_WHERE(pred)                                                                    \
+    {                                                                                           \
+        _Pragma("unroll") for (int kk_ = 0; kk_ < K; ++kk_) {                                   \
+            unsigned m_ = __ballot_sync(GQW_FULL, pred[kk_]);                                   \
+            while (m_) {                                                                        \
+                const int b_ = __ffs(m_) - 1;                                                   \
+                m_ &= m_ - 1;                                                                   \
+                GQM_STAT(6, 1);                                                                 \
+                GQT_SCAN(GQW_LANES * kk_ + b_);                                                 \
+            }                                                                                   \
+        }                                                                                       \
+    }
+
+    for (int x = lane; x < n; x += GQW_LANES) {
+        f.base[x] = (i16)x; f.par[x] = -1; f.label[x] = L_NONE; f.mark[x] = 0; f.top[x] = (i16)x;
+    }
+    for (int i = lane; i < FT::nb; i += GQW_LANES) f.bused[i] = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { vtop[k] = lane + GQW_LANES * k; vlab[k] = L_NONE; }
+    __syncwarp();
+
+#pragma unroll 1
+    for (int rk = 0; rk < K; ++rk) {
+        unsigned rm;
+        {
+            bool isfree = false;
+#pragma unroll
+            for (int k = 0; k < K; ++k) if (k == rk) isfree = (freebits >> k) & 1;
+            rm = __ballot_sync(GQW_FULL, isfree);
+        }
+        while (rm) {
+            const int rb = __ffs(rm) - 1;
+            rm &= rm - 1;
+            const int root = GQW_LANES * rk + rb;
+            if (f.mate[root] != -1) continue;   // became the far end of an earlier augmenting path
+            // ---- phase: one alternating tree rooted at root
+            D = 0;
+            bool news[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                tm[k] = SL_INF; slfrom[k] = -1; news[k] = false;
+                if (lane + GQW_LANES * k == root) { vlab[k] = L_S; f.label[root] = L_S; }
+            }
+            __syncwarp();
+            GQM_STAT(6, 1);
+            GQT_SCAN(root);
+            int vfree = -1;
+            for (int guard = 0;; ++guard) {
+                if (guard > 8 * (cap + FT::nb) + 64) return 3;
+                // ---- earliest event: key = time << 10 | type << 8 | arg
+                unsigned best = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const unsigned v = (unsigned)(lane + GQW_LANES * k);
+                    if (vlab[k] != L_T && tm[k] < SL_INF)
+                        best = min(best, ((unsigned)tm[k] << 10) | (vlab[k] == L_S ? 0x100u : 0u) | v);
+                    if (vlab[k] == L_S && b4[k] < SL_INF)
+                        best = min(best, ((unsigned)(b4[k] - yb[k]) << 10) | 0x300u | v);
+                }
+                for (int i = lane; i < bhi; i += GQW_LANES)
+                    if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] == L_T)
+                        best = min(best, ((unsigned)(f.yb[i] >> 1) << 10) | 0x200u | (unsigned)i);
+                best = __reduce_min_sync(GQW_FULL, best);
+                GQM_STAT(0, 1);
+                if (best == 0xffffffffu) return 1;
+                const i32 t = (i32)(best >> 10);
+                const int type = (best >> 8) & 3;
+                const int arg = best & 0xff;
+                int src = -1;
+                if (type < 2) GQT_SEL(slfrom, arg, src);
+                if (type == 1 && f.top[src] == f.top[arg]) {
+                    GQM_STAT(1, 1);
+                    // stale: the source was swallowed by the target's blossom -> recompute the best
+                    // edge from the outer vertices of other nodes into arg
+                    const int tv = f.top[arg];
+                    i32 yv;
+                    GQT_SEL(yb, arg, yv);
+                    yv += D;
+                    const uint32_t ro = (uint32_t)def[arg] * N;
+                    unsigned bb = 0xffffffffu;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int u = lane + GQW_LANES * k;
+                        const u16 wt = dist[ro + dj[k]];
+                        if (u < n && vlab[k] == L_S && vtop[k] != tv && wt != W_INF) {
+                            const i32 s = 4 * (i32)wt - yv - (yb[k] + D);
+                            bb = min(bb, ((unsigned)s << 8) | (unsigned)u);
+                        }
+                    }
+                    bb = __reduce_min_sync(GQW_FULL, bb);
+                    const i32 nt = bb == 0xffffffffu ? SL_INF : D + (i32)(bb >> 9);
+                    const int nf = bb == 0xffffffffu ? -1 : (int)(bb & 0xff);
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        if (lane + GQW_LANES * k == arg) { tm[k] = nt; slfrom[k] = nf; }
+                    continue;
+                }
+                D = t;
+                if (type == 0) {
+                    // ---- an outer vertex reaches an unlabelled node
+                    const int v = arg, u = src;
+                    const int tn = f.top[v];
+                    const int m = f.mate[f.base[tn]];
+                    if (m < 0) {
+                        // the node is free (m == -1, a plain vertex) or sits on the boundary
+                        // (m == -2): u takes it over; a boundary match is simply released
+                        GQM_STAT(4, 1);
+                        if (lane == 0) { gqr::rebase(f, tn, v); gqr::augment(f, u, v); }
+                        if (m == -1) vfree = v;
+                        break;
+                    }
+                    GQM_STAT(2, 1);
+                    const int sn = f.top[m];
+                    if (lane == 0) {
+                        f.label[tn] = L_T; f.pu[tn] = (i16)u; f.pv[tn] = (i16)v; f.label[sn] = L_S;
+                        if (tn >= cap) f.yb[tn - cap] += 2 * D;   // z = zb - 2D from now on
+                        if (sn >= cap) f.yb[sn - cap] -= 2 * D;   // z = zb + 2D
+                    }
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        news[k] = false;
+                        if (lane + GQW_LANES * k < n) {
+                            if (vtop[k] == tn) {
+                                vlab[k] = L_T; yb[k] += D;
+                                if (tm[k] < SL_INF) tm[k] -= D;
+                            } else if (vtop[k] == sn) {
+                                vlab[k] = L_S; yb[k] -= D; news[k] = true;
+                                if (tm[k] < SL_INF) tm[k] = (tm[k] + D) >> 1;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                } else if (type == 3) {
+                    // ---- an outer vertex reaches the boundary: the tree augments onto it
+                    GQM_STAT(4, 1);
+                    if (lane == 0) gqr::augment_half(f, arg, -2);
+                    break;
+                } else if (type == 1) {
+                    GQM_STAT(3, 1);
+                    // ---- odd cycle: shrink
+                    const int v = arg, u = src;
+                    for (int x = lane; x < cap + bhi; x += GQW_LANES) f.mark[x] = 0;
+                    __syncwarp();
+                    int b = 0;
+                    if (lane == 0) {
+                        b = gqr::shrink(f, u, v);
+                        if (b >= 0) {
+                            // children that are blossoms freeze their dual at its current value
+                            int c = f.first[b - cap];
+                            const int c0 = c;
+                            do {
+                                if (c >= cap) f.yb[c - cap] += f.label[c] == L_S ? 2 * D : -2 * D;
+                                c = f.nxt[c];
+                            } while (c != c0);
+                            f.yb[b - cap] = -2 * D;   // z = zb + 2D = 0 now
+                        }
+                    }
+                    b = __shfl_sync(GQW_FULL, b, 0);
+                    if (b < 0) return 2;
+                    bhi = max(bhi, b - cap + 1);
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        news[k] = false;
+                        const int x = lane + GQW_LANES * k;
+                        if (x < n && f.par[vtop[k]] == b) {
+                            if (vlab[k] == L_T) {
+                                news[k] = true;
+                                yb[k] -= 2 * D;
+                                if (tm[k] < SL_INF) tm[k] = D + (tm[k] >> 1);
+                            }
+                            vtop[k] = b; vlab[k] = L_S;
+                            f.top[x] = (i16)b;
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    GQM_STAT(7, 1);
+                    // ---- an inner blossom's dual reached zero: expand
+                    const int b = cap + arg;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int x = lane + GQW_LANES * k;
+                        if (x < n && vtop[k] == b) {
+                            int c = x;
+                            while (f.par[c] != b) c = f.par[c];
+                            vtop[k] = c;
+                            f.top[x] = (i16)c;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int fst = f.first[b - cap];
+                        gqr::expand_relabel(f, b);
+                        int c = fst;
+                        do {
+                            if (c >= cap && f.label[c] != L_NONE) f.yb[c - cap] += f.label[c] == L_S ? -2 * D : 2 * D;
+                            c = f.nxt[c];
+                        } while (c != fst);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int x = lane + GQW_LANES * k;
+                        news[k] = false;
+                        if (x < n && vlab[k] == L_T) {
+                            const int nl = f.label[vtop[k]];
+                            if (nl == L_S) {
+                                news[k] = true; yb[k] -= 2 * D;
+                                if (tm[k] < SL_INF) tm[k] = D + (tm[k] >> 1);
+                            } else if (nl == L_NONE) {
+                                yb[k] -= D;
+                                if (tm[k] < SL_INF) tm[k] += D;
+                            }
+                            vlab[k] = nl;
+                        }
+                    }
+                }
+                GQT_SCAN_WHERE(news);
+            }
+            // ---- phase end: the tree dissolves, duals leave the clock
+            __syncwarp();
+            for (int i = lane; i < bhi; i += GQW_LANES) {
+                if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] != L_NONE)
+                    f.yb[i] += f.label[cap + i] == L_S ? 2 * D : -2 * D;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int x = lane + GQW_LANES * k;
+                if (vlab[k] != L_NONE) {
+                    yb[k] += vlab[k] == L_S ? D : -D;
+                    vlab[k] = L_NONE;
+                    f.label[vtop[k]] = L_NONE;
+                }
+                if (x == root || x == vfree) freebits &= ~GQW_BIT(k);
+            }
+            __syncwarp();
+        }
+    }
+    return 0;
+#undef GQT_YACT
+#undef GQT_SEL
+#undef GQT_SCAN
+#undef GQT_SCAN_WHERE
+}
+
+// ---- one shot: defects def[0..n) (32*(K-1) < n <= 32*K on the device) -> prediction mask, weight.
+// Returns the solver's code (0 ok).
+template <int K, class FT>
+__device__ __forceinline__ int decode_shot(const Tables &T, FT &f, const u16 *def, const int n,
+                                           const int lane, const bool want_weight, uint32_t *pm_out, int *wt_out) {
+    const u16 *__restrict__ dist = T.dist;
+    const uint32_t N = T.N;
+    const uint32_t bro = T.D * N;
+    uint32_t dj[K];
+    i32 b4[K], yb[K];
+    unsigned key[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int v = lane + GQW_LANES * k;
+        dj[k] = v < n ? def[v] : T.D;     // padding slots sit on the boundary column, never read back
+        const uint32_t bb = dist[bro + dj[k]];
+        b4[k] = (v >= n || bb == (uint32_t)W_INF) ? SL_INF : 4 * (i32)bb;
+        key[k] = 0xffffffffu;
+    }
+    // ---- nearest other defect of every defect: key = distance << 8 | index (diagonal = W_INF)
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+        const uint32_t ro = (uint32_t)def[i] * N;
+#pragma unroll
+        for (int k = 0; k < K; ++k) key[k] = min(key[k], ((unsigned)dist[ro + dj[k]] << 8) | (unsigned)i);
+    }
+    // ---- dual start, boundary matches, mutual nearest neighbours
+    gqw_mask freebits = 0;
+    bool onb[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int v = lane + GQW_LANES * k;
+        const uint32_t wmin = key[k] >> 8;
+        const i32 y2 = wmin >= (uint32_t)W_INF ? SL_INF : 2 * (i32)wmin;
+        onb[k] = b4[k] < SL_INF && b4[k] <= y2;
+        yb[k] = onb[k] ? b4[k] : (y2 < SL_INF ? y2 : 0);
+        if (v < n) f.stk[v] = (i16)((onb[k] || y2 == SL_INF) ? -1 : (int)(key[k] & 0xff));
+    }
+    __syncwarp();
+    int m0[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int v = lane + GQW_LANES * k;
+        m0[k] = -3;
+        if (v < n) {
+            const int u = f.stk[v];
+            int m = onb[k] ? -2 : -1;
+            if (u >= 0 && f.stk[u] == v) m = u;
+            m0[k] = m;
+            if (m == -1) freebits |= GQW_BIT(k);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; ++k) if (m0[k] != -3) f.mate[lane + GQW_LANES * k] = (i16)m0[k];
+    __syncwarp();
+#ifdef GQ_MT_STATS
+    {
+        int nf = 0;
+        for (int k = 0; k < K; ++k) nf += (int)((freebits >> k) & 1);
+        GQM_STAT(8, __reduce_add_sync(GQW_FULL, nf));
+        GQM_STAT(9, 1);
+    }
+#endif
+    const int any_free = __any_sync(GQW_FULL, freebits != 0);
+    int rc = 0;
+    if (any_free) rc = solve_tree<K>(f, dist, N, def, n, lane, dj, b4, yb, freebits);
+    __syncwarp();
+    uint32_t pm = 0;
+    int wt = 0, bad = 0;
+    if (rc == 0) {
+        const uint8_t *bobs = T.pobs + (size_t)bro;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int v = lane + GQW_LANES * k;
+            if (v < n) {
+                const int j = f.mate[v];
+                if (j == -2) {
+                    if (b4[k] == SL_INF) bad = 1;
+                    pm ^= bobs[dj[k]];
+                    wt += b4[k] >> 2;
+                } else if (j < 0) {
+                    bad = 1;
+                } else if (j > v) {
+                    const uint32_t at = (uint32_t)def[j] * N + dj[k];
+                    pm ^= T.pobs[at];
+                    if (want_weight) {
+                        const uint32_t d = dist[at];
+                        if (d >= (uint32_t)W_INF) bad = 1;
+                        wt += (int)d;
+                    }
+                }
+            }
+        }
+        pm = __reduce_xor_sync(GQW_FULL, pm);
+        wt = __reduce_add_sync(GQW_FULL, wt);
+        if (__any_sync(GQW_FULL, bad)) rc = 1;
+    }
+    *pm_out = pm;
+    *wt_out = wt;
+    return rc;
+}
+
+}  // namespace gqt

@@ -26,6 +26,7 @@ __device__ unsigned long long gq_stats[16];
 #include "blossom_regs.cuh"
 #include "blossom_warp.cuh"
 #include "gq_common.h"
+#include "match_tree.cuh"
 
 #ifndef GQ_PER_SM
 #define GQ_PER_SM 4
@@ -306,6 +307,73 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
     }
 }
 
+// ---- first tier: single-tree blossom phases on the defect set, weights gathered straight from the
+// distance table (match_tree.cuh).  Handles shots with at most MT_CAP defects; the rest (and any shot
+// the solver gives up on) go to the overflow list and climb the ladder of the older tiers.
+#ifndef GQ_MT_PER_SM
+#define GQ_MT_PER_SM 4
+#endif
+static constexpr int MT_CAP = 128;
+struct MtWarpMem {
+    gqr::StaticForest<MT_CAP> F;
+    uint16_t def[MT_CAP];
+};
+
+__global__ void __launch_bounds__(256, GQ_MT_PER_SM) match_mt_kernel(MatchArgs a) {
+    extern __shared__ __align__(16) char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    MtWarpMem &M = reinterpret_cast<MtWarpMem *>(smem)[wib];
+    gqt::Tables T;
+    T.dist = a.dist; T.pobs = a.pobs; T.D = a.D; T.N = a.D + 1;
+    const bool want_weight = a.weight_out != nullptr;
+
+    for (uint64_t item = warp; item < a.nitems; item += nwarps) {
+        const uint64_t shot = a.list ? a.list[item] : item;
+        const int n0 = gqt::extract_defects(a.dets + shot * a.DW, a.DW, a.D, lane, M.def, MT_CAP);
+        uint32_t pm = 0;
+        int wt = 0, rc = 0;
+        if (n0 > MT_CAP) rc = 4;
+#if !defined(GQ_MT_ALLK) && !defined(GQ_MT_K34)
+        else if (n0 > 0) rc = gqt::decode_shot<4>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
+#elif defined(GQ_MT_K34)
+        else if (n0 > 96) rc = gqt::decode_shot<4>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
+        else if (n0 > 0) rc = gqt::decode_shot<3>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
+#else
+        else if (n0 > 96) rc = gqt::decode_shot<4>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
+        else if (n0 > 64) rc = gqt::decode_shot<3>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
+        else if (n0 > 32) rc = gqt::decode_shot<2>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
+        else if (n0 > 0) rc = gqt::decode_shot<1>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
+#endif
+        if (rc >= 2) {
+            // more defects than this tier holds, or the solver gave up: hand the shot to the next tier
+            if (lane == 0) {
+                uint32_t idx = atomicAdd(&a.overflow[0], 1u);
+                atomicMax(&a.overflow[1], (uint32_t)n0);
+                if (idx < a.overflow_cap) a.overflow[2 + idx] = (uint32_t)shot;
+            }
+            __syncwarp();
+            continue;
+        }
+        if (rc == 0 && a.corr_out && n0 > 0) {
+            uint32_t *corr_row = a.corr_out + shot * a.EW;
+            for (int i = lane; i < n0; i += 32) {
+                const int j = M.F.mate[i];
+                if (j == -2) walk_path(a, M.def[i], a.D, corr_row);
+                else if (j > i) walk_path(a, M.def[i], M.def[j], corr_row);
+            }
+        }
+        if (lane == 0) {
+            a.pred[shot * a.OW] = rc == 0 ? pm : 0u;
+            for (uint32_t w = 1; w < a.OW; ++w) a.pred[shot * a.OW + w] = 0u;
+            if (a.weight_out) a.weight_out[shot] = rc == 0 ? wt : -1;
+            if (a.flags_out) a.flags_out[shot] = (uint8_t)(rc == 0 ? 0 : 1);
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host: graph + tables
 // ------------------------------------------------------------------------------------------------
@@ -437,6 +505,7 @@ int gq_matching_create(gq_dec *dec) {
         for (auto &t : th) t.join();
     }
     if (too_far) GQ_FAIL(GQ_E_UNSUPPORTED, "matching decoder: path lengths exceed 16 bits; lower weight_levels");
+    for (uint32_t s = 0; s < N; ++s) dist[(size_t)s * N + s] = 0xFFFFu;   // no self pairs (match_tree.cuh relies on it)
     dec->max_dist = *std::max_element(row_max.begin(), row_max.end());
     // ---- capacities: expected defect count from the DEM
     std::vector<double> keep(D, 1.0);
@@ -478,6 +547,7 @@ int gq_matching_create(gq_dec *dec) {
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    GQ_CUDA(cudaFuncSetAttribute(match_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem))));
     dec->overflow_cap = 1u << 20;
     GQ_CUDA(cudaMalloc((void **)&dec->d_overflow, 2 * (2 + (size_t)dec->overflow_cap) * 4));
     return GQ_OK;
@@ -521,7 +591,54 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
         b.list = nullptr; b.nitems = ns;
         int K = (int)dec->fast_cap / 32;
         int cur = 0;
+        if (!dec->params.legacy_tiers) {
+            // ---- first tier: multi-tree solver, no weight matrix (match_mt.cuh)
+            const int nwarps = dem->num_sms * GQ_MT_PER_SM * 8;
+            GQ_CUDA(cudaMemsetAsync(ovf_buf[cur], 0, 8, dem->stream));
+            b.cap = MT_CAP;
+            b.ws = nullptr; b.ws_stride = 0;
+            b.overflow = ovf_buf[cur]; b.overflow_cap = dec->overflow_cap;
+            int blocks = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)nwarps / 8);
+            match_mt_kernel<<<blocks, 256, 8 * sizeof(MtWarpMem), dem->stream>>>(b);
+            GQ_CUDA(cudaGetLastError());
+            ++*launches;
+            uint32_t ovf[2];
+            GQ_CUDA(cudaMemcpyAsync(ovf, ovf_buf[cur], 8, cudaMemcpyDeviceToHost, dem->stream));
+            GQ_CUDA(cudaStreamSynchronize(dem->stream));
+            if (ovf[0] == 0) continue;
+            if (ovf[0] > dec->overflow_cap) GQ_FAIL(GQ_E_INTERNAL, "matching decoder: overflow list overrun");
+            b.list = ovf_buf[cur] + 2; b.nitems = ovf[0];
+            cur ^= 1;
+            K = 1;
+            while (K < 8 && 32 * K - 1 < (int)ovf[1]) K *= 2;
+            if (32 * K - 1 < (int)ovf[1]) K = 16;   // beyond the register tiers: straight to the memory tier
+        }
         for (;;) {
+            if (K > 8) {
+                uint32_t ovf[2];
+                GQ_CUDA(cudaMemcpyAsync(ovf, b.list - 2, 8, cudaMemcpyDeviceToHost, dem->stream));
+                GQ_CUDA(cudaStreamSynchronize(dem->stream));
+                int bigcap = std::min<int>(even_up((int)ovf[1] + 1), (int)dec->max_cap);
+                size_t wsb = warp_ws_bytes(bigcap);
+                int nw = (int)std::min<uint64_t>(ovf[0], (uint64_t)dem->num_sms * 8);
+                size_t budget = (size_t)8 << 30;
+                nw = (int)std::max<size_t>(1, std::min<size_t>(nw, budget / wsb));
+                nw = std::max(8, (nw / 8) * 8);
+                if (wsb * nw > dec->ws_big_bytes) {
+                    cudaFree(dec->d_ws_big);
+                    dec->d_ws_big = nullptr; dec->ws_big_bytes = 0;
+                    GQ_CUDA(cudaMalloc(&dec->d_ws_big, wsb * nw));
+                    dec->ws_big_bytes = wsb * nw;
+                }
+                MatchArgs c = b;
+                c.cap = (uint32_t)bigcap;
+                c.ws = (char *)dec->d_ws_big; c.ws_stride = wsb;
+                c.overflow = nullptr; c.overflow_cap = 0;
+                match_kernel<<<nw / 8, 256, 0, dem->stream>>>(c);
+                GQ_CUDA(cudaGetLastError());
+                ++*launches;
+                break;
+            }
             // ---- one pass of tier K over the current item list
             const int cap = 32 * K;
             const int per_sm = K <= 4 ? GQ_PER_SM : 2;

@@ -49,7 +49,8 @@ typedef struct gq_decoder_params {
     int32_t with_corrections;  /* matching: keep the next-hop table so corrections can be emitted */
     int32_t bp_max_iter;       /* BP: iteration cap (default 30) */
     float bp_alpha;            /* BP: min-sum normalisation factor (default 0.9) */
-    int32_t reserved[8];
+    int32_t legacy_tiers;      /* matching: 1 = skip the multi-tree first tier (A/B testing only) */
+    int32_t reserved[7];
 } gq_decoder_params;
 
 typedef struct gq_dem_info {

@@ -145,3 +145,97 @@ def test_decoder_matching_core_handles_missing_edges(hostsim):
     mate = np.zeros(4, dtype=np.int16)
     wt = ctypes.c_longlong(0)
     assert hostsim.hostsim_solve(4, w.ctypes.data, mate.ctypes.data, ctypes.byref(wt)) == 1
+
+
+# ------------------------------------------------------------------------------------------
+# first tier of the CUDA matching decoder (match_tree.cuh) compiled for the host with one lane
+# ------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def tree_hostsim():
+    so = os.path.join(ROOT, "tests", "hostsim", "libmthostsim.so")
+    srcs = [os.path.join(ROOT, "tests", "hostsim", f) for f in ("mt_hostsim.cpp", "warp_sim.h")]
+    srcs += [os.path.join(ROOT, "graphqec_b200", "csrc", f) for f in ("match_tree.cuh", "blossom_regs.cuh")]
+    if not os.path.exists(so) or max(os.path.getmtime(s) for s in srcs) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
+    lib = ctypes.CDLL(so)
+    lib.hostsim_mt_decode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_long] + [ctypes.c_void_p] * 4
+    lib.hostsim_mt_stats.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    return lib
+
+
+def _device_tables(orc):
+    """the (D+1)x(D+1) distance / path-observable tables in the layout matching.cu uploads"""
+    T, P = orc.dist_table(), orc.parity_table()
+    D = orc.nd
+    far = T >= 0xFFFF
+    dist = np.full((D + 1, D + 1), 0xFFFF, np.uint16)
+    pobs = np.zeros((D + 1, D + 1), np.uint8)
+    Tc = np.where(far | (T < 0), 0xFFFF, T).astype(np.uint16)
+    dist[:D, :D] = Tc[:, :D]; dist[:D, D] = Tc[:, D]; dist[D, :D] = Tc[:, D]
+    pobs[:D, :D] = P[:, :D]; pobs[:D, D] = P[:, D]; pobs[D, :D] = P[:, D]
+    np.fill_diagonal(dist, 0xFFFF)
+    return dist, pobs
+
+
+def _tree_decode(lib, orc, dets_b8):
+    D = orc.nd
+    dist, pobs = _device_tables(orc)
+    n = dets_b8.shape[0]
+    DW = (D + 31) // 32
+    rows = np.zeros((n, DW * 4), np.uint8)
+    rows[:, :dets_b8.shape[1]] = dets_b8
+    rows32 = np.ascontiguousarray(rows).view(np.uint32)
+    pred = np.zeros(n, np.uint32); wt = np.zeros(n, np.int32); rc = np.zeros(n, np.int32)
+    lib.hostsim_mt_decode(D, dist.ctypes.data, pobs.ctypes.data, DW, rows32.ctypes.data, n,
+                          pred.ctypes.data, wt.ctypes.data, rc.ctypes.data, None)
+    return pred, wt, rc
+
+
+def test_tree_tier_is_exact_on_surface_code_shots(tree_hostsim):
+    code = RotatedSurfaceCode(distance=5, depolarize1_rate=0.01, depolarize2_rate=0.01)
+    code.build_memory_circuit(number_of_rounds=5, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model(decompose_errors=True)
+    orc = po.MwpmOracle(dem)
+    dets, _ = po.sample(dem, 3, 3000)
+    pred, wt, rc = _tree_decode(tree_hostsim, orc, dets)
+    opred, owt = orc.decode_batch(dets, return_weights=True)
+    assert (rc == 0).all()
+    assert (wt == owt).all()          # every matching is a minimum-weight one
+    assert (pred != opred).mean() < 0.01   # equal-weight optima may differ in the predicted observable
+
+
+def test_tree_tier_is_exact_on_random_graphs_with_blossoms(tree_hostsim):
+    rng = np.random.default_rng(5)
+    stats = (ctypes.c_longlong * 16)()
+    tree_hostsim.hostsim_mt_stats(stats, 1)
+    for trial in range(60):
+        D = int(rng.integers(6, 40))
+        edges = []
+        for u in range(D):
+            for v in range(u + 1, D):
+                if v == u + 1 or rng.random() < 0.25:     # the chain keeps the graph connected
+                    edges.append((u, v, 0.1, int(rng.integers(0, 2))))
+        for u in range(D):
+            if u == 0 or rng.random() < (0.3 if trial % 3 else 0.05):
+                edges.append((u, -1, 0.1, int(rng.integers(0, 2))))
+        hi = int(rng.choice([3, 10, 1000]))
+        w = rng.integers(1, hi + 1, size=len(edges))
+        orc = po.MwpmOracle(edges=edges, num_detectors=D, num_observables=1, int_weights=w)
+        bits = (rng.random((200, D)) < rng.choice([0.15, 0.4, 0.8])).astype(np.uint8)
+        dets = np.packbits(bits, axis=1, bitorder="little")
+        pred, wt, rc = _tree_decode(tree_hostsim, orc, dets)
+        opred, owt = orc.decode_batch(dets, return_weights=True)
+        assert (rc == 0).all() and (wt == owt).all(), (trial, np.where(wt != owt)[0][:5])
+    tree_hostsim.hostsim_mt_stats(stats, 0)
+    assert stats[3] > 200 and stats[7] > 5    # shrinks and expands were exercised
+
+
+def test_tree_tier_reports_undecodable_syndromes(tree_hostsim):
+    # detector 2 has no edge at all: a defect there cannot be matched
+    orc = po.MwpmOracle(edges=[(0, 1, 0.1, 0), (0, -1, 0.1, 1)], num_detectors=3, num_observables=1,
+                        int_weights=np.array([5, 7]))
+    dets = np.packbits(np.array([[1, 1, 0], [0, 0, 1], [1, 0, 1]], np.uint8), axis=1, bitorder="little")
+    pred, wt, rc = _tree_decode(tree_hostsim, orc, dets)
+    assert rc.tolist() == [0, 1, 1] and wt[0] == 5
