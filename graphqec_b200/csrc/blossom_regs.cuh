@@ -92,24 +92,33 @@ struct StaticForest {
 };
 
 // ---------------------------------------------------------------- lane 0 forest surgery
+// inlined by default (measured: out-of-line calls cost more in spills than they save in fetch);
+// -DGQ_SURGERY_INLINE=__noinline__ keeps them out of the event loop for experiments
+#ifndef GQ_SURGERY_INLINE
+#define GQ_SURGERY_INLINE __forceinline__
+#endif
 // (FT = Forest or StaticForest<CAP>)
 template <class FT>
-__device__ __forceinline__ void rebase(FT &f, int x0, int a0) {
+__device__ GQ_SURGERY_INLINE void rebase(FT &f, int x0, int a0) {
     const int cap = f.cap;
     int sp = 0;
     f.stk[sp++] = (i16)x0; f.stk[sp++] = (i16)a0;
+#pragma unroll 1
     while (sp) {
         int a = f.stk[--sp];
         int B = f.stk[--sp];
         if (B < cap || f.base[B] == a) continue;
         int c = a;
+#pragma unroll 1
         while (f.par[c] != B) c = f.par[c];
         f.stk[sp++] = (i16)c; f.stk[sp++] = (i16)a;
         const int fst = f.first[B - cap];
         int steps = 0;
+#pragma unroll 1
         for (int t = c; t != fst; t = f.prv[t]) ++steps;
         int p = c;
         if ((steps & 1) == 0) {
+#pragma unroll 1
             while (p != fst) {
                 int q1 = f.prv[p], q2 = f.prv[q1];
                 int a2 = f.eu[q2], a1 = f.ev[q2];
@@ -119,6 +128,7 @@ __device__ __forceinline__ void rebase(FT &f, int x0, int a0) {
                 p = q2;
             }
         } else {
+#pragma unroll 1
             while (p != fst) {
                 int q1 = f.nxt[p], q2 = f.nxt[q1];
                 int a1 = f.eu[q1], a2 = f.ev[q1];
@@ -134,8 +144,9 @@ __device__ __forceinline__ void rebase(FT &f, int x0, int a0) {
 }
 
 template <class FT>
-__device__ __forceinline__ void augment(FT &f, int u, int v) {
+__device__ GQ_SURGERY_INLINE void augment(FT &f, int u, int v) {
     int a = u, nm = v;
+#pragma unroll 1
     for (;;) {
         int x = f.top[a];
         int m = f.mate[f.base[x]];
@@ -153,8 +164,9 @@ __device__ __forceinline__ void augment(FT &f, int u, int v) {
 // one side of an augmentation between two trees: flip the path from outer vertex u to its root and
 // point u at its new mate nm (the caller's other half sets mate[nm])
 template <class FT>
-__device__ __forceinline__ void augment_half(FT &f, int u, int nm0) {
+__device__ GQ_SURGERY_INLINE void augment_half(FT &f, int u, int nm0) {
     int a = u, nm = nm0, first = 1;
+#pragma unroll 1
     for (;;) {
         int x = f.top[a];
         int m = f.mate[f.base[x]];
@@ -181,19 +193,23 @@ __device__ __forceinline__ int parent_S(FT &f, int x, int *tnode) {
 
 // mark[] must be zero on entry
 template <class FT>
-__device__ __forceinline__ int shrink(FT &f, int u, int v) {
+__device__ GQ_SURGERY_INLINE int shrink(FT &f, int u, int v) {
     const int cap = f.cap, nb = f.nb;
     int xu = f.top[u], xv = f.top[v];
+#pragma unroll 1
     for (int x = xu; x >= 0;) { f.mark[x] = 1; int t; x = parent_S(f, x, &t); }
     int lca = xv;
+#pragma unroll 1
     while (!f.mark[lca]) { int t; lca = parent_S(f, lca, &t); }
     int b = -1;
+#pragma unroll 1
     for (int i = 0; i < nb; ++i) if (!f.bused[i]) { b = cap + i; f.bused[i] = 1; break; }
     if (b < 0) return -1;
     f.nxt[lca] = (i16)lca; f.prv[lca] = (i16)lca;
     {
         int have = 0, bu = 0, bv = 0, first_iter = 1;
         int x = xu;
+#pragma unroll 1
         while (x != lca) {
             int t; int up = parent_S(f, x, &t);
             int old = f.nxt[lca];
@@ -213,6 +229,7 @@ __device__ __forceinline__ int shrink(FT &f, int u, int v) {
         int tail = f.prv[lca];
         f.eu[tail] = (i16)u; f.ev[tail] = (i16)v;
         int x = xv;
+#pragma unroll 1
         while (x != lca) {
             int t; int up = parent_S(f, x, &t);
             f.nxt[tail] = (i16)x; f.prv[x] = (i16)tail;
@@ -229,23 +246,27 @@ __device__ __forceinline__ int shrink(FT &f, int u, int v) {
     f.yb[b - cap] = 0;
     f.label[b] = L_S;
     int c = lca;
+#pragma unroll 1
     do { f.par[c] = (i16)b; c = f.nxt[c]; } while (c != lca);
     return b;
 }
 
 // relabel the children of T blossom b (top[] of its vertices already points at them)
 template <class FT>
-__device__ __forceinline__ void expand_relabel(FT &f, int b) {
+__device__ GQ_SURGERY_INLINE void expand_relabel(FT &f, int b) {
     const int cap = f.cap;
     const int fst = f.first[b - cap];
     const int c = f.top[f.pv[b]];
     int steps = 0;
+#pragma unroll 1
     for (int t = c; t != fst; t = f.prv[t]) ++steps;
     int x = fst;
+#pragma unroll 1
     do { f.label[x] = L_NONE; int nx = f.nxt[x]; f.par[x] = -1; x = nx; } while (x != fst);
     f.label[c] = L_T; f.pu[c] = f.pu[b]; f.pv[c] = f.pv[b];
     int p = c;
     if ((steps & 1) == 0) {
+#pragma unroll 1
         while (p != fst) {
             int s = f.prv[p], t = f.prv[s];
             f.label[s] = L_S;
@@ -253,6 +274,7 @@ __device__ __forceinline__ void expand_relabel(FT &f, int b) {
             p = t;
         }
     } else {
+#pragma unroll 1
         while (p != fst) {
             int s = f.nxt[p], t = f.nxt[s];
             f.label[s] = L_S;

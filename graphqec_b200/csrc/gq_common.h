@@ -84,6 +84,7 @@ struct gq_dec {
     size_t ws_fast_bytes = 0, ws_big_bytes = 0;
     int nwarps_fast = 0, nwarps_big = 0;
     uint32_t *d_overflow = nullptr;    // [1 + capacity] overflow shot list
+    uint32_t *d_lists = nullptr;       // first tier: [16] class counts, then one shot list per class
     uint32_t overflow_cap = 0;
     // ---- BP
     uint32_t *d_chk_ptr = nullptr, *d_chk_var = nullptr, *d_var_ptr = nullptr, *d_var_edge = nullptr;

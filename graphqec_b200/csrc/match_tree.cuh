@@ -62,9 +62,9 @@ using gqr::SL_INF;
 using gqr::W_INF;
 
 struct Tables {
-    const u16 *dist;       // [D+1][D+1], row D = distances to the boundary, diagonal = W_INF
-    const uint8_t *pobs;   // [D+1][D+1] observable mask of the shortest path
-    uint32_t N, D;         // N = D + 1
+    const u16 *dist;       // [N][N]: row/column D = the boundary, D + 1 = nothing (all W_INF); diagonal = W_INF
+    const uint8_t *pobs;   // [N][N] observable mask of the shortest path
+    uint32_t N, D;         // N = D + 2
 };
 
 // ---- defect list of one bit-packed syndrome row (ascending detector index); returns the count,
@@ -117,19 +117,37 @@ __device__ __forceinline__ int sel_slot(const TV (&arr)[K], const int slot) {
 // yb[] feasible duals (quadrupled units, even), b4[] 4*boundary distance or SL_INF, freebits = slots
 // of this lane that are free.  Out: f.mate[].  Returns 0 ok, 1 no perfect matching, 2 blossom ids
 // exhausted, 3 step guard.
+//
+// Per-slot event keys (one register each, so the search is a handful of integer minima):
+//   ek = pending edge event  : time << 10 | type << 8 | vertex   (type 0: an outer vertex reaches this
+//        unlabelled vertex, 1: outer-outer edge turns tight); an inner vertex keeps its frozen slack
+//        in the same layout with bit 31 set, which also keeps it out of the search
+//   bk = boundary event of an outer vertex: time << 10 | 3 << 8 | vertex
+// Labels in registers: 0 unlabelled, +1 outer, -1 inner, so that y = yb + vlab * D.
+static const unsigned EK_NONE = 0x7fffffffu;   // no pending edge event (time field all ones)
+static const unsigned EK_FROZEN = 0x80000000u;
+
+__device__ __forceinline__ bool ek_has(unsigned ek) { return (ek | 0x800003ffu) != 0xffffffffu; }
+__device__ __forceinline__ i32 ek_time(unsigned ek) { return (i32)((ek >> 10) & 0x1fffffu); }
+
 template <int K, class FT>
 __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, const uint32_t N,
                                           const u16 *def, const int n, const int lane,
                                           const uint32_t (&dj)[K], const i32 (&b4)[K], i32 (&yb)[K],
                                           gqw_mask freebits) {
     constexpr int cap = FT::cap;
-    i32 tm[K];
+    unsigned ek[K], bk[K];
     int slfrom[K], vtop[K], vlab[K];
     i32 D = 0;
     int bhi = 0;
 
-#define GQT_YACT(k_, t_) (yb[k_] + (vlab[k_] == L_S ? (t_) : (vlab[k_] == L_T ? -(t_) : 0)))
 #define GQT_SEL(arr, u, out) { out = __shfl_sync(GQW_FULL, sel_slot<K>(arr, (u) >> GQW_LOG), (u) & (GQW_LANES - 1)); }
+// slot k_ turns outer at clock D (yb[k_] already rebased): boundary event, key bits
+#define GQT_MAKE_OUTER(k_)                                                                      \
+    {                                                                                           \
+        vlab[k_] = 1;                                                                           \
+        bk[k_] = b4[k_] < SL_INF ? (((unsigned)(b4[k_] - yb[k_]) << 10) | 0x300u | (unsigned)(lane + GQW_LANES * (k_))) : 0xffffffffu; \
+    }
 // scan the row of outer vertex u_ (its dual is yb + D): offer its edges to every vertex of other nodes
 #define GQT_SCAN(u_)                                                                            \
     {                                                                                           \
@@ -140,44 +158,51 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
         yu_ += D;                                                                               \
         const uint32_t ro_ = (uint32_t)def[su_] * N;                                            \
         _Pragma("unroll") for (int k_ = 0; k_ < K; ++k_) {                                      \
-            const u16 wt_ = dist[ro_ + dj[k_]];                                                 \
-            if (lane + GQW_LANES * k_ < n && vtop[k_] != tu_ && wt_ != W_INF) {                 \
-                const i32 s_ = 4 * (i32)wt_ - yu_ - GQT_YACT(k_, D);                            \
-                const i32 c_ = vlab[k_] == L_NONE ? D + s_ : (vlab[k_] == L_S ? D + (s_ >> 1) : s_); \
-                if (c_ < tm[k_]) { tm[k_] = c_; slfrom[k_] = su_; }                             \
-            }                                                                                   \
+            const i32 wt_ = (i32)dist[ro_ + dj[k_]];                                            \
+            const i32 s_ = 4 * wt_ - yu_ - (yb[k_] + vlab[k_] * D);                             \
+            const unsigned v_ = (unsigned)(lane + GQW_LANES * k_);                              \
+            const unsigned nk_ = vlab[k_] == 0 ? (((unsigned)(D + s_) << 10) | v_)              \
+                               : (vlab[k_] > 0 ? (((unsigned)(D + (s_ >> 1)) << 10) | 0x100u | v_) \
+                                               : (((unsigned)s_ << 10) | EK_FROZEN | v_));      \
+            if (wt_ != (i32)W_INF && vtop[k_] != tu_ && nk_ < ek[k_]) { ek[k_] = nk_; slfrom[k_] = su_; } \
         }                                                                                       \
     }
+// scan every vertex flagged in pred[]; one instance of the scan body (code size), slots walked by a
+// runtime loop over their ballots
 #define GQT_SCAN_WHERE(pred)                                                                    \
     {                                                                                           \
-        _Pragma("unroll") for (int kk_ = 0; kk_ < K; ++kk_) {                                   \
-            unsigned m_ = __ballot_sync(GQW_FULL, pred[kk_]);                                   \
-            while (m_) {                                                                        \
-                const int b_ = __ffs(m_) - 1;                                                   \
-                m_ &= m_ - 1;                                                                   \
-                GQM_STAT(6, 1);                                                                 \
-                GQT_SCAN(GQW_LANES * kk_ + b_);                                                 \
+        unsigned pm_[K];                                                                        \
+        unsigned any_ = 0;                                                                      \
+        _Pragma("unroll") for (int kk_ = 0; kk_ < K; ++kk_) { pm_[kk_] = __ballot_sync(GQW_FULL, pred[kk_]); any_ |= pm_[kk_]; } \
+        if (any_) {                                                                             \
+            _Pragma("unroll 1") for (int kk_ = 0; kk_ < K; ++kk_) {                             \
+                unsigned m_ = (unsigned)sel_slot<K>(pm_, kk_);                                  \
+                _Pragma("unroll 1") while (m_) {                                                \
+                    const int b_ = __ffs(m_) - 1;                                               \
+                    m_ &= m_ - 1;                                                               \
+                    GQM_STAT(6, 1);                                                             \
+                    GQT_SCAN(GQW_LANES * kk_ + b_);                                             \
+                }                                                                               \
             }                                                                                   \
         }                                                                                       \
     }
 
+#pragma unroll 1
     for (int x = lane; x < n; x += GQW_LANES) {
         f.base[x] = (i16)x; f.par[x] = -1; f.label[x] = L_NONE; f.mark[x] = 0; f.top[x] = (i16)x;
     }
+#pragma unroll 1
     for (int i = lane; i < FT::nb; i += GQW_LANES) f.bused[i] = 0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) { vtop[k] = lane + GQW_LANES * k; vlab[k] = L_NONE; }
+    for (int k = 0; k < K; ++k) {
+        vtop[k] = lane + GQW_LANES * k; vlab[k] = 0;
+        bk[k] = 0xffffffffu;
+    }
     __syncwarp();
 
 #pragma unroll 1
     for (int rk = 0; rk < K; ++rk) {
-        unsigned rm;
-        {
-            bool isfree = false;
-#pragma unroll
-            for (int k = 0; k < K; ++k) if (k == rk) isfree = (freebits >> k) & 1;
-            rm = __ballot_sync(GQW_FULL, isfree);
-        }
+        unsigned rm = __ballot_sync(GQW_FULL, (freebits >> rk) & 1);
         while (rm) {
             const int rb = __ffs(rm) - 1;
             rm &= rm - 1;
@@ -188,36 +213,35 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
             bool news[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                tm[k] = SL_INF; slfrom[k] = -1; news[k] = false;
-                if (lane + GQW_LANES * k == root) { vlab[k] = L_S; f.label[root] = L_S; }
+                ek[k] = EK_NONE; slfrom[k] = -1;
+                news[k] = lane + GQW_LANES * k == root;
+                if (news[k]) { GQT_MAKE_OUTER(k); f.label[root] = L_S; }
             }
             __syncwarp();
-            GQM_STAT(6, 1);
-            GQT_SCAN(root);
             int vfree = -1;
             for (int guard = 0;; ++guard) {
+                GQT_SCAN_WHERE(news);
                 if (guard > 8 * (cap + FT::nb) + 64) return 3;
-                // ---- earliest event: key = time << 10 | type << 8 | arg
+                // ---- earliest event
                 unsigned best = 0xffffffffu;
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const unsigned v = (unsigned)(lane + GQW_LANES * k);
-                    if (vlab[k] != L_T && tm[k] < SL_INF)
-                        best = min(best, ((unsigned)tm[k] << 10) | (vlab[k] == L_S ? 0x100u : 0u) | v);
-                    if (vlab[k] == L_S && b4[k] < SL_INF)
-                        best = min(best, ((unsigned)(b4[k] - yb[k]) << 10) | 0x300u | v);
+                for (int k = 0; k < K; ++k) best = min(best, min(ek[k], bk[k]));
+                if (bhi) {
+#pragma unroll 1
+                    for (int i = lane; i < bhi; i += GQW_LANES)
+                        if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] == L_T)
+                            best = min(best, ((unsigned)(f.yb[i] >> 1) << 10) | 0x200u | (unsigned)i);
                 }
-                for (int i = lane; i < bhi; i += GQW_LANES)
-                    if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] == L_T)
-                        best = min(best, ((unsigned)(f.yb[i] >> 1) << 10) | 0x200u | (unsigned)i);
                 best = __reduce_min_sync(GQW_FULL, best);
                 GQM_STAT(0, 1);
-                if (best == 0xffffffffu) return 1;
+                if (best >= 0x7ffffc00u) return 1;
                 const i32 t = (i32)(best >> 10);
                 const int type = (best >> 8) & 3;
                 const int arg = best & 0xff;
                 int src = -1;
                 if (type < 2) GQT_SEL(slfrom, arg, src);
+#pragma unroll
+                for (int k = 0; k < K; ++k) news[k] = false;
                 if (type == 1 && f.top[src] == f.top[arg]) {
                     GQM_STAT(1, 1);
                     // stale: the source was swallowed by the target's blossom -> recompute the best
@@ -230,19 +254,18 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     unsigned bb = 0xffffffffu;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        const int u = lane + GQW_LANES * k;
-                        const u16 wt = dist[ro + dj[k]];
-                        if (u < n && vlab[k] == L_S && vtop[k] != tv && wt != W_INF) {
-                            const i32 s = 4 * (i32)wt - yv - (yb[k] + D);
-                            bb = min(bb, ((unsigned)s << 8) | (unsigned)u);
-                        }
+                        const i32 wt = (i32)dist[ro + dj[k]];
+                        const i32 s = 4 * wt - yv - (yb[k] + D);
+                        if (vlab[k] > 0 && vtop[k] != tv && wt != (i32)W_INF)
+                            bb = min(bb, ((unsigned)s << 8) | (unsigned)(lane + GQW_LANES * k));
                     }
                     bb = __reduce_min_sync(GQW_FULL, bb);
-                    const i32 nt = bb == 0xffffffffu ? SL_INF : D + (i32)(bb >> 9);
-                    const int nf = bb == 0xffffffffu ? -1 : (int)(bb & 0xff);
 #pragma unroll
                     for (int k = 0; k < K; ++k)
-                        if (lane + GQW_LANES * k == arg) { tm[k] = nt; slfrom[k] = nf; }
+                        if (lane + GQW_LANES * k == arg) {
+                            ek[k] = bb == 0xffffffffu ? EK_NONE : ((((unsigned)D + (bb >> 9)) << 10) | 0x100u | (unsigned)arg);
+                            slfrom[k] = bb == 0xffffffffu ? -1 : (int)(bb & 0xff);
+                        }
                     continue;
                 }
                 D = t;
@@ -268,15 +291,13 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     }
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        news[k] = false;
-                        if (lane + GQW_LANES * k < n) {
-                            if (vtop[k] == tn) {
-                                vlab[k] = L_T; yb[k] += D;
-                                if (tm[k] < SL_INF) tm[k] -= D;
-                            } else if (vtop[k] == sn) {
-                                vlab[k] = L_S; yb[k] -= D; news[k] = true;
-                                if (tm[k] < SL_INF) tm[k] = (tm[k] + D) >> 1;
-                            }
+                        if (vtop[k] == tn) {
+                            vlab[k] = -1; yb[k] += D;
+                            ek[k] = ek_has(ek[k]) ? ((ek[k] - ((unsigned)D << 10)) | EK_FROZEN) : 0xffffffffu;
+                        } else if (vtop[k] == sn) {
+                            yb[k] -= D; news[k] = true;
+                            if (ek_has(ek[k])) ek[k] = ((unsigned)((ek_time(ek[k]) + D) >> 1) << 10) | 0x100u | (unsigned)(lane + GQW_LANES * k);
+                            GQT_MAKE_OUTER(k);
                         }
                     }
                     __syncwarp();
@@ -289,6 +310,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     GQM_STAT(3, 1);
                     // ---- odd cycle: shrink
                     const int v = arg, u = src;
+#pragma unroll 1
                     for (int x = lane; x < cap + bhi; x += GQW_LANES) f.mark[x] = 0;
                     __syncwarp();
                     int b = 0;
@@ -311,15 +333,15 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     __syncwarp();
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        news[k] = false;
                         const int x = lane + GQW_LANES * k;
                         if (x < n && f.par[vtop[k]] == b) {
-                            if (vlab[k] == L_T) {
+                            if (vlab[k] < 0) {
                                 news[k] = true;
                                 yb[k] -= 2 * D;
-                                if (tm[k] < SL_INF) tm[k] = D + (tm[k] >> 1);
+                                ek[k] = ek_has(ek[k]) ? (((unsigned)(D + (ek_time(ek[k]) >> 1)) << 10) | 0x100u | (unsigned)x) : EK_NONE;
+                                GQT_MAKE_OUTER(k);
                             }
-                            vtop[k] = b; vlab[k] = L_S;
+                            vtop[k] = b;
                             f.top[x] = (i16)b;
                         }
                     }
@@ -331,8 +353,9 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const int x = lane + GQW_LANES * k;
-                        if (x < n && vtop[k] == b) {
+                        if (vtop[k] == b) {
                             int c = x;
+#pragma unroll 1
                             while (f.par[c] != b) c = f.par[c];
                             vtop[k] = c;
                             f.top[x] = (i16)c;
@@ -352,35 +375,37 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const int x = lane + GQW_LANES * k;
-                        news[k] = false;
-                        if (x < n && vlab[k] == L_T) {
+                        if (x < n && vlab[k] < 0) {
                             const int nl = f.label[vtop[k]];
                             if (nl == L_S) {
                                 news[k] = true; yb[k] -= 2 * D;
-                                if (tm[k] < SL_INF) tm[k] = D + (tm[k] >> 1);
+                                ek[k] = ek_has(ek[k]) ? (((unsigned)(D + (ek_time(ek[k]) >> 1)) << 10) | 0x100u | (unsigned)x) : EK_NONE;
+                                GQT_MAKE_OUTER(k);
                             } else if (nl == L_NONE) {
                                 yb[k] -= D;
-                                if (tm[k] < SL_INF) tm[k] += D;
+                                ek[k] = ek_has(ek[k]) ? (((unsigned)(D + ek_time(ek[k])) << 10) | (unsigned)x) : EK_NONE;
+                                vlab[k] = 0;
                             }
-                            vlab[k] = nl;
                         }
                     }
                 }
-                GQT_SCAN_WHERE(news);
             }
             // ---- phase end: the tree dissolves, duals leave the clock
             __syncwarp();
-            for (int i = lane; i < bhi; i += GQW_LANES) {
-                if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] != L_NONE)
-                    f.yb[i] += f.label[cap + i] == L_S ? 2 * D : -2 * D;
+            if (bhi) {
+#pragma unroll 1
+                for (int i = lane; i < bhi; i += GQW_LANES) {
+                    if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] != L_NONE)
+                        f.yb[i] += f.label[cap + i] == L_S ? 2 * D : -2 * D;
+                }
+                __syncwarp();
             }
-            __syncwarp();
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int x = lane + GQW_LANES * k;
-                if (vlab[k] != L_NONE) {
-                    yb[k] += vlab[k] == L_S ? D : -D;
-                    vlab[k] = L_NONE;
+                if (vlab[k] != 0) {
+                    yb[k] += vlab[k] * D;
+                    vlab[k] = 0; bk[k] = 0xffffffffu;
                     f.label[vtop[k]] = L_NONE;
                 }
                 if (x == root || x == vfree) freebits &= ~GQW_BIT(k);
@@ -389,8 +414,8 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
         }
     }
     return 0;
-#undef GQT_YACT
 #undef GQT_SEL
+#undef GQT_MAKE_OUTER
 #undef GQT_SCAN
 #undef GQT_SCAN_WHERE
 }
@@ -409,9 +434,9 @@ __device__ __forceinline__ int decode_shot(const Tables &T, FT &f, const u16 *de
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int v = lane + GQW_LANES * k;
-        dj[k] = v < n ? def[v] : T.D;     // padding slots sit on the boundary column, never read back
+        dj[k] = v < n ? def[v] : T.D + 1;     // padding slots read the "nothing" column: all infinite
         const uint32_t bb = dist[bro + dj[k]];
-        b4[k] = (v >= n || bb == (uint32_t)W_INF) ? SL_INF : 4 * (i32)bb;
+        b4[k] = bb == (uint32_t)W_INF ? SL_INF : 4 * (i32)bb;
         key[k] = 0xffffffffu;
     }
     // ---- nearest other defect of every defect: key = distance << 8 | index (diagonal = W_INF)
@@ -419,7 +444,7 @@ __device__ __forceinline__ int decode_shot(const Tables &T, FT &f, const u16 *de
     for (int i = 0; i < n; ++i) {
         const uint32_t ro = (uint32_t)def[i] * N;
 #pragma unroll
-        for (int k = 0; k < K; ++k) key[k] = min(key[k], ((unsigned)dist[ro + dj[k]] << 8) | (unsigned)i);
+        for (int k = 0; k < K; ++k) key[k] = min(key[k], (unsigned)dist[ro + dj[k]] * 256u + (unsigned)i);
     }
     // ---- dual start, boundary matches, mutual nearest neighbours
     gqw_mask freebits = 0;

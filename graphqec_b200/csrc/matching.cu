@@ -41,6 +41,7 @@ struct MatchArgs {
     const uint32_t *list;     // optional shot list (overflow pass)
     uint64_t nitems;
     uint32_t D, DW, OW, EW;
+    uint32_t N;               // row stride of the dist / pobs / next tables = D + 2 (D = boundary, D + 1 = nothing)
     uint32_t cap;             // even; real defects handled: cap - 1
     const uint16_t *dist;
     const uint8_t *pobs;
@@ -53,7 +54,7 @@ struct MatchArgs {
 };
 
 __device__ __forceinline__ void walk_path(const MatchArgs &a, uint32_t cur, uint32_t target, uint32_t *corr_row) {
-    const uint32_t N = a.D + 1;
+    const uint32_t N = a.N;
     for (uint32_t guard = 0; guard <= a.D && cur != target; ++guard) {
         uint32_t nx = a.next[(size_t)target * N + cur];
         if (nx == 0xFFFFu) nx = a.D;  // hop onto the boundary
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) match_kernel(MatchArgs a) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t N = a.D + 1;
+    const uint32_t N = a.N;
     const int cap = (int)a.cap;
     char *mem = a.ws + warp * a.ws_stride;
     gqb::Solver S;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t N = a.D + 1;
+    const uint32_t N = a.N;
     const size_t per_warp = gqr::forest_bytes(CAP) + (size_t)CAP * 4;
     char *mem = smem + (size_t)wib * per_warp;
     const gqr::Forest F = gqr::forest_bind(mem, CAP);
@@ -308,56 +309,102 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
 }
 
 // ---- first tier: single-tree blossom phases on the defect set, weights gathered straight from the
-// distance table (match_tree.cuh).  Handles shots with at most MT_CAP defects; the rest (and any shot
-// the solver gives up on) go to the overflow list and climb the ladder of the older tiers.
+// distance table (match_tree.cuh).  The solver keeps K = ceil(n / 32) vertices per lane in registers,
+// and the kernels are instruction-fetch bound, so every K gets its own kernel (a fused switch over K
+// ran 2.4x slower: four solver bodies thrash the instruction cache) and classify_kernel sorts the
+// shots of a slice into per-K lists first.  Shots with more than MT_CAP defects, and any shot the
+// solver gives up on, go to the overflow list and climb the ladder of the older tiers.
 #ifndef GQ_MT_PER_SM
 #define GQ_MT_PER_SM 4
 #endif
 static constexpr int MT_CAP = 128;
+static constexpr int MT_CLASSES = 4;     // K = 1 .. 4
+
+template <int K>
 struct MtWarpMem {
-    gqr::StaticForest<MT_CAP> F;
-    uint16_t def[MT_CAP];
+    gqr::StaticForest<32 * K> F;
+    uint16_t def[32 * K];
 };
 
-__global__ void __launch_bounds__(256, GQ_MT_PER_SM) match_mt_kernel(MatchArgs a) {
+// counts[0..3]: shots of class K = 1..4, lists[c][...]: their indices; defect-free shots are answered
+// here; overflow (> MT_CAP defects) is appended to the ladder's list
+struct ClassifyArgs {
+    const uint32_t *dets;
+    uint32_t *pred;
+    int32_t *weight_out;
+    uint8_t *flags_out;
+    uint32_t *counts;          // [MT_CLASSES]
+    uint32_t *lists;           // [MT_CLASSES][list_stride]
+    uint32_t list_stride;
+    uint32_t *overflow;
+    uint32_t overflow_cap;
+    uint32_t nshots, D, DW, OW;
+};
+
+__global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < a.nshots; base += gridDim.x * blockDim.x) {
+        const uint32_t shot = base + threadIdx.x;
+        int n = -1;
+        if (shot < a.nshots) {
+            const uint32_t *row = a.dets + (size_t)shot * a.DW;
+            n = 0;
+            for (uint32_t w = 0; w + 1 < a.DW; ++w) n += __popc(row[w]);
+            uint32_t last = row[a.DW - 1];
+            if (a.D & 31) last &= (1u << (a.D & 31)) - 1;
+            n += __popc(last);
+        }
+        const int cls = n < 0 ? -1 : (n == 0 ? -2 : (n > MT_CAP ? MT_CLASSES : (n - 1) >> 5));
+        if (cls == -2) {
+            for (uint32_t w = 0; w < a.OW; ++w) a.pred[(size_t)shot * a.OW + w] = 0u;
+            if (a.weight_out) a.weight_out[shot] = 0;
+            if (a.flags_out) a.flags_out[shot] = 0;
+        }
+#pragma unroll
+        for (int c = 0; c <= MT_CLASSES; ++c) {
+            const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+            if (m == 0) continue;
+            uint32_t pos = 0;
+            if (lane == __ffs(m) - 1) pos = atomicAdd(c < MT_CLASSES ? &a.counts[c] : &a.overflow[0], (uint32_t)__popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1));
+            if (cls == c) {
+                if (c < MT_CLASSES) a.lists[(size_t)c * a.list_stride + pos] = shot;
+                else if (pos < a.overflow_cap) a.overflow[2 + pos] = shot;
+            }
+        }
+        if (cls == MT_CLASSES) atomicMax(&a.overflow[1], (uint32_t)n);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, GQ_MT_PER_SM) match_tree_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    MtWarpMem &M = reinterpret_cast<MtWarpMem *>(smem)[wib];
+    MtWarpMem<K> &M = reinterpret_cast<MtWarpMem<K> *>(smem)[wib];
     gqt::Tables T;
-    T.dist = a.dist; T.pobs = a.pobs; T.D = a.D; T.N = a.D + 1;
+    T.dist = a.dist; T.pobs = a.pobs; T.D = a.D; T.N = a.N;
     const bool want_weight = a.weight_out != nullptr;
 
-    for (uint64_t item = warp; item < a.nitems; item += nwarps) {
-        const uint64_t shot = a.list ? a.list[item] : item;
-        const int n0 = gqt::extract_defects(a.dets + shot * a.DW, a.DW, a.D, lane, M.def, MT_CAP);
+    for (uint32_t item = warp; item < a.nitems; item += nwarps) {
+        const uint32_t shot = a.list[item];
+        const int n0 = gqt::extract_defects(a.dets + (size_t)shot * a.DW, a.DW, a.D, lane, M.def, 32 * K);
         uint32_t pm = 0;
-        int wt = 0, rc = 0;
-        if (n0 > MT_CAP) rc = 4;
-#if !defined(GQ_MT_ALLK) && !defined(GQ_MT_K34)
-        else if (n0 > 0) rc = gqt::decode_shot<4>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
-#elif defined(GQ_MT_K34)
-        else if (n0 > 96) rc = gqt::decode_shot<4>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
-        else if (n0 > 0) rc = gqt::decode_shot<3>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
-#else
-        else if (n0 > 96) rc = gqt::decode_shot<4>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
-        else if (n0 > 64) rc = gqt::decode_shot<3>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
-        else if (n0 > 32) rc = gqt::decode_shot<2>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
-        else if (n0 > 0) rc = gqt::decode_shot<1>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
-#endif
+        int wt = 0;
+        int rc = (n0 > 32 * K || n0 <= 32 * (K - 1)) ? 4 : gqt::decode_shot<K>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
         if (rc >= 2) {
-            // more defects than this tier holds, or the solver gave up: hand the shot to the next tier
+            // the solver gave up (or the list lied about the defect count): hand the shot to the ladder
             if (lane == 0) {
                 uint32_t idx = atomicAdd(&a.overflow[0], 1u);
                 atomicMax(&a.overflow[1], (uint32_t)n0);
-                if (idx < a.overflow_cap) a.overflow[2 + idx] = (uint32_t)shot;
+                if (idx < a.overflow_cap) a.overflow[2 + idx] = shot;
             }
             __syncwarp();
             continue;
         }
-        if (rc == 0 && a.corr_out && n0 > 0) {
-            uint32_t *corr_row = a.corr_out + shot * a.EW;
+        if (rc == 0 && a.corr_out) {
+            uint32_t *corr_row = a.corr_out + (size_t)shot * a.EW;
             for (int i = lane; i < n0; i += 32) {
                 const int j = M.F.mate[i];
                 if (j == -2) walk_path(a, M.def[i], a.D, corr_row);
@@ -365,8 +412,8 @@ __global__ void __launch_bounds__(256, GQ_MT_PER_SM) match_mt_kernel(MatchArgs a
             }
         }
         if (lane == 0) {
-            a.pred[shot * a.OW] = rc == 0 ? pm : 0u;
-            for (uint32_t w = 1; w < a.OW; ++w) a.pred[shot * a.OW + w] = 0u;
+            a.pred[(size_t)shot * a.OW] = rc == 0 ? pm : 0u;
+            for (uint32_t w = 1; w < a.OW; ++w) a.pred[(size_t)shot * a.OW + w] = 0u;
             if (a.weight_out) a.weight_out[shot] = rc == 0 ? wt : -1;
             if (a.flags_out) a.flags_out[shot] = (uint8_t)(rc == 0 ? 0 : 1);
         }
@@ -446,9 +493,12 @@ int gq_matching_create(gq_dec *dec) {
     }
     // ---- all-pairs shortest paths: row s = Dijkstra tree rooted at s (row D: rooted at the boundary)
     const bool want_next = dec->params.with_corrections != 0;
-    std::vector<uint16_t> dist((size_t)N * N, 0xFFFFu), nexttab;
-    std::vector<uint8_t> pobs((size_t)N * N, 0);
-    if (want_next) nexttab.assign((size_t)N * N, 0xFFFFu);
+    // tables have one more row / column than nodes: index D + 1 is "nothing" (all distances infinite),
+    // the column that padding slots of the first tier read
+    const uint32_t NT = D + 2;
+    std::vector<uint16_t> dist((size_t)NT * NT, 0xFFFFu), nexttab;
+    std::vector<uint8_t> pobs((size_t)NT * NT, 0);
+    if (want_next) nexttab.assign((size_t)NT * NT, 0xFFFFu);
     std::vector<uint32_t> row_max(N, 0);
     std::atomic<bool> too_far(false);
     auto worker = [&](uint32_t s_begin, uint32_t s_end) {
@@ -485,9 +535,9 @@ int gq_matching_create(gq_dec *dec) {
             for (uint32_t t = 0; t < N; ++t) {
                 if (d[t] == ~0ull) continue;
                 if (d[t] >= 0xFFFEull) { too_far = true; continue; }
-                dist[(size_t)s * N + t] = (uint16_t)d[t];
-                pobs[(size_t)s * N + t] = po[t];
-                if (want_next && t != s) nexttab[(size_t)s * N + t] = pr[t] == D ? 0xFFFFu : (uint16_t)pr[t];
+                dist[(size_t)s * NT + t] = (uint16_t)d[t];
+                pobs[(size_t)s * NT + t] = po[t];
+                if (want_next && t != s) nexttab[(size_t)s * NT + t] = pr[t] == D ? 0xFFFFu : (uint16_t)pr[t];
                 mx = std::max<uint32_t>(mx, (uint32_t)d[t]);
             }
             row_max[s] = mx;
@@ -505,7 +555,7 @@ int gq_matching_create(gq_dec *dec) {
         for (auto &t : th) t.join();
     }
     if (too_far) GQ_FAIL(GQ_E_UNSUPPORTED, "matching decoder: path lengths exceed 16 bits; lower weight_levels");
-    for (uint32_t s = 0; s < N; ++s) dist[(size_t)s * N + s] = 0xFFFFu;   // no self pairs (match_tree.cuh relies on it)
+    for (uint32_t s = 0; s < N; ++s) dist[(size_t)s * NT + s] = 0xFFFFu;   // no self pairs (match_tree.cuh relies on it)
     dec->max_dist = *std::max_element(row_max.begin(), row_max.end());
     // ---- capacities: expected defect count from the DEM
     std::vector<double> keep(D, 1.0);
@@ -547,7 +597,11 @@ int gq_matching_create(gq_dec *dec) {
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    GQ_CUDA(cudaFuncSetAttribute(match_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem))));
+    GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<1>))));
+    GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<2>))));
+    GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<3>))));
+    GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<4>))));
+    GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << 20) + 16) * 4));
     dec->overflow_cap = 1u << 20;
     GQ_CUDA(cudaMalloc((void **)&dec->d_overflow, 2 * (2 + (size_t)dec->overflow_cap) * 4));
     return GQ_OK;
@@ -563,7 +617,7 @@ extern "C" void gq_debug_stats(unsigned long long *out, int reset) {
 void gq_matching_destroy(gq_dec *dec) {
     cudaFree(dec->d_dist); cudaFree(dec->d_pobs); cudaFree(dec->d_next);
     cudaFree(dec->d_adj_ptr); cudaFree(dec->d_adj_node); cudaFree(dec->d_adj_edge);
-    cudaFree(dec->d_ws_fast); cudaFree(dec->d_ws_big); cudaFree(dec->d_overflow);
+    cudaFree(dec->d_ws_fast); cudaFree(dec->d_ws_big); cudaFree(dec->d_overflow); cudaFree(dec->d_lists);
 }
 
 int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
@@ -575,6 +629,7 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
     a.dets = dets_sm; a.pred = pred_sm; a.weight_out = weight_out; a.flags_out = flags_out;
     a.corr_out = corr_out;
     a.D = dem->D; a.DW = dem->DW; a.OW = dem->OW; a.EW = (dec->num_edges + 31) / 32;
+    a.N = dem->D + 2;
     a.dist = dec->d_dist; a.pobs = dec->d_pobs; a.next = dec->d_next;
     a.adj_ptr = dec->d_adj_ptr; a.adj_node = dec->d_adj_node; a.adj_edge = dec->d_adj_edge;
     // the overflow lists are bounded: process in slices so they can never overrun
@@ -592,16 +647,39 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
         int K = (int)dec->fast_cap / 32;
         int cur = 0;
         if (!dec->params.legacy_tiers) {
-            // ---- first tier: multi-tree solver, no weight matrix (match_mt.cuh)
+            // ---- first tier: per-K kernels over the lists classify_kernel builds (match_tree.cuh)
             const int nwarps = dem->num_sms * GQ_MT_PER_SM * 8;
+            uint32_t *d_counts = dec->d_lists;
+            uint32_t *d_lists = dec->d_lists + 16;
             GQ_CUDA(cudaMemsetAsync(ovf_buf[cur], 0, 8, dem->stream));
+            GQ_CUDA(cudaMemsetAsync(d_counts, 0, 16 * 4, dem->stream));
+            ClassifyArgs ca;
+            ca.dets = b.dets; ca.pred = b.pred; ca.weight_out = b.weight_out; ca.flags_out = b.flags_out;
+            ca.counts = d_counts; ca.lists = d_lists; ca.list_stride = (uint32_t)slice;
+            ca.overflow = ovf_buf[cur]; ca.overflow_cap = dec->overflow_cap;
+            ca.nshots = (uint32_t)ns; ca.D = a.D; ca.DW = a.DW; ca.OW = a.OW;
+            classify_kernel<<<(int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)dem->num_sms * 8), 256, 0, dem->stream>>>(ca);
+            GQ_CUDA(cudaGetLastError());
+            ++*launches;
+            uint32_t counts[MT_CLASSES];
+            GQ_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(counts), cudaMemcpyDeviceToHost, dem->stream));
+            GQ_CUDA(cudaStreamSynchronize(dem->stream));
             b.cap = MT_CAP;
             b.ws = nullptr; b.ws_stride = 0;
             b.overflow = ovf_buf[cur]; b.overflow_cap = dec->overflow_cap;
-            int blocks = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)nwarps / 8);
-            match_mt_kernel<<<blocks, 256, 8 * sizeof(MtWarpMem), dem->stream>>>(b);
-            GQ_CUDA(cudaGetLastError());
-            ++*launches;
+            static const int order[MT_CLASSES] = {2, 3, 1, 0};   // biggest class first
+            for (int oi = 0; oi < MT_CLASSES; ++oi) {
+                const int c = order[oi];
+                if (counts[c] == 0) continue;
+                b.list = d_lists + (size_t)c * slice; b.nitems = counts[c];
+                int blocks = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)nwarps / 8);
+                if (c == 0) match_tree_kernel<1><<<blocks, 256, 8 * sizeof(MtWarpMem<1>), dem->stream>>>(b);
+                else if (c == 1) match_tree_kernel<2><<<blocks, 256, 8 * sizeof(MtWarpMem<2>), dem->stream>>>(b);
+                else if (c == 2) match_tree_kernel<3><<<blocks, 256, 8 * sizeof(MtWarpMem<3>), dem->stream>>>(b);
+                else match_tree_kernel<4><<<blocks, 256, 8 * sizeof(MtWarpMem<4>), dem->stream>>>(b);
+                GQ_CUDA(cudaGetLastError());
+                ++*launches;
+            }
             uint32_t ovf[2];
             GQ_CUDA(cudaMemcpyAsync(ovf, ovf_buf[cur], 8, cudaMemcpyDeviceToHost, dem->stream));
             GQ_CUDA(cudaStreamSynchronize(dem->stream));

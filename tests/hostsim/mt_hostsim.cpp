@@ -13,13 +13,13 @@ static inline void gqm_stat_add(int i, long long x) { gqm_stats[i] += x; }
 #define HS_CAP 128
 #endif
 
-// dist/pobs: [(D+1)][(D+1)] tables as the CUDA decoder builds them (row/col D = boundary).
+// dist/pobs: [D+2][D+2] tables as the CUDA decoder builds them (row/col D = boundary, D+1 = nothing).
 // dets: nshots rows of DW uint32 words.  Outputs per shot: prediction mask, weight, return code
 // (0 ok, 1 no perfect matching, 2/3 solver gave up, 4 more defects than the tier holds).
 extern "C" int hostsim_mt_decode(int D, const uint16_t *dist, const uint8_t *pobs, int DW, const uint32_t *dets,
                                  long nshots, uint32_t *pred, int32_t *weight, int32_t *rcs, int16_t *mates_out) {
     gqt::Tables T;
-    T.dist = dist; T.pobs = pobs; T.D = (uint32_t)D; T.N = (uint32_t)D + 1;
+    T.dist = dist; T.pobs = pobs; T.D = (uint32_t)D; T.N = (uint32_t)D + 2;
     std::vector<uint16_t> def(HS_CAP);
     static gqr::StaticForest<HS_CAP> F;
     for (long s = 0; s < nshots; ++s) {

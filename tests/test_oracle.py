@@ -166,12 +166,12 @@ def tree_hostsim():
 
 
 def _device_tables(orc):
-    """the (D+1)x(D+1) distance / path-observable tables in the layout matching.cu uploads"""
+    """the (D+2)x(D+2) distance / path-observable tables in the layout matching.cu uploads"""
     T, P = orc.dist_table(), orc.parity_table()
     D = orc.nd
     far = T >= 0xFFFF
-    dist = np.full((D + 1, D + 1), 0xFFFF, np.uint16)
-    pobs = np.zeros((D + 1, D + 1), np.uint8)
+    dist = np.full((D + 2, D + 2), 0xFFFF, np.uint16)
+    pobs = np.zeros((D + 2, D + 2), np.uint8)
     Tc = np.where(far | (T < 0), 0xFFFF, T).astype(np.uint16)
     dist[:D, :D] = Tc[:, :D]; dist[:D, D] = Tc[:, D]; dist[D, :D] = Tc[:, D]
     pobs[:D, :D] = P[:, :D]; pobs[:D, D] = P[:, D]; pobs[D, :D] = P[:, D]
