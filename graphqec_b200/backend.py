@@ -79,6 +79,7 @@ SIGNATURES = {
     "gq_count_errors": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "gq_collect": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, POINTER(c_uint64 * 3)]),
     "gq_last_timing": (c_int, [c_void_p, POINTER(c_double * 8)]),
+    "gq_last_kernel_profile": (c_int, [c_void_p, POINTER(c_double * 4)]),
     "gq_sync": (c_int, [c_void_p]),
 }
 
@@ -299,6 +300,11 @@ class DecoderHandle:
         rc = load_library().gq_collect(self.demh._h, self._h, seed, shot0, nshots, max_errors, ctypes.byref(out))
         _check(rc, "gq_collect")
         return int(out[0]), int(out[1]), int(out[2])
+
+    def last_kernel_profile(self) -> dict:
+        t = (c_double * 4)()
+        _check(load_library().gq_last_kernel_profile(self._h, ctypes.byref(t)), "gq_last_kernel_profile")
+        return {"ms": t[0], "launches": int(t[1]), "shots": int(t[2]), "K": int(t[3])}
 
     def last_timing(self) -> dict:
         t = (c_double * 8)()

@@ -139,6 +139,7 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
     GQ_CUDA(cudaEventCreate(&e2)); GQ_CUDA(cudaEventCreate(&e3));
     double t_h2d = 0, t_dec = 0, t_d2h = 0;
     int launches = 0;
+    memset(dec->kprof, 0, sizeof(dec->kprof));
     int rc = ensure_scratch(dec, std::min(chunk, nshots));
     if (rc) return rc;
     if (dec->b8_bytes < chunk * (db + ob)) {
@@ -193,6 +194,7 @@ extern "C" int gq_collect(gq_dem *dem, gq_dec *dec, uint64_t seed, uint64_t shot
     GQ_CUDA(cudaMemsetAsync(dec->d_count, 0, 8, dem->stream));
     double t_s = 0, t_d = 0, t_c = 0;
     int launches = 0;
+    memset(dec->kprof, 0, sizeof(dec->kprof));
     uint64_t done = 0, errors = 0;
     while (done < nshots) {
         uint64_t ns = std::min(chunk, nshots - done);
@@ -223,6 +225,12 @@ extern "C" int gq_collect(gq_dem *dem, gq_dec *dec, uint64_t seed, uint64_t shot
     out[0] = done; out[1] = errors; out[2] = 0;
     double *t = dec->timing;
     t[0] = t_s; t[1] = t_d; t[2] = t_c; t[3] = t_s + t_d + t_c; t[4] = 0; t[5] = 8; t[6] = launches; t[7] = 0;
+    return GQ_OK;
+}
+
+extern "C" int gq_last_kernel_profile(const gq_dec *dec, double out[4]) {
+    if (!dec || !out) GQ_FAIL(GQ_E_INVALID, "gq_last_kernel_profile: NULL argument");
+    memcpy(out, dec->kprof, sizeof(double) * 4);
     return GQ_OK;
 }
 

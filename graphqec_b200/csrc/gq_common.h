@@ -67,6 +67,8 @@ struct gq_dec {
     int kind = 0;
     gq_decoder_params params{};
     double timing[8] = {0};
+    double kprof[4] = {0};             // dominant first-tier kernel of the last call: {ms, launches, shots, K}
+    cudaEvent_t kev0 = nullptr, kev1 = nullptr;
     // ---- matching
     uint32_t num_edges = 0, num_boundary = 0;
     std::vector<uint32_t> eu, ev, ew;

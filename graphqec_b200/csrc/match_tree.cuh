@@ -105,10 +105,19 @@ __device__ __forceinline__ int sel_slot(const TV (&arr)[K], const int slot) {
     if constexpr (K == 1) return (int)arr[0];
     else if constexpr (K == 2) return (slot & 1) ? (int)arr[1] : (int)arr[0];
     else if constexpr (K == 3) return (slot & 2) ? (int)arr[2] : ((slot & 1) ? (int)arr[1] : (int)arr[0]);
-    else if constexpr (K == 4) {
-        const int lo = (slot & 1) ? (int)arr[1] : (int)arr[0];
-        const int hi = (slot & 1) ? (int)arr[3] : (int)arr[2];
-        return (slot & 2) ? hi : lo;
+    else if constexpr (K <= 8) {
+        const int lo = (slot & 2) ? ((slot & 1) ? (int)arr[3] : (int)arr[2]) : ((slot & 1) ? (int)arr[1] : (int)arr[0]);
+        if constexpr (K == 4) return lo;
+        else {
+            int hi = (int)arr[4];
+            if constexpr (K >= 6) hi = (slot & 1) ? (int)arr[5] : hi;
+            if constexpr (K >= 7) {
+                int h2 = (int)arr[6];
+                if constexpr (K >= 8) h2 = (slot & 1) ? (int)arr[7] : h2;
+                hi = (slot & 2) ? h2 : hi;
+            }
+            return (slot & 4) ? hi : lo;
+        }
     } else return (int)arr[slot];
 }
 

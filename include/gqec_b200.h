@@ -49,7 +49,7 @@ typedef struct gq_decoder_params {
     int32_t with_corrections;  /* matching: keep the next-hop table so corrections can be emitted */
     int32_t bp_max_iter;       /* BP: iteration cap (default 30) */
     float bp_alpha;            /* BP: min-sum normalisation factor (default 0.9) */
-    int32_t legacy_tiers;      /* matching: 1 = skip the multi-tree first tier (A/B testing only) */
+    int32_t legacy_tiers;      /* matching: 1 = skip the first tier (A/B testing only) */
     int32_t reserved[7];
 } gq_decoder_params;
 
@@ -151,6 +151,11 @@ int gq_collect(gq_dem *dem, gq_dec *dec, uint64_t seed, uint64_t shot0, uint64_t
 /* device-time of the last gq_collect / gq_decode_b8 call on this decoder, per stage, milliseconds:
  * {sample, decode, count, total, h2d, d2h, kernel launches} */
 int gq_last_timing(const gq_dec *dec, double out_ms[8]);
+
+/* the dominant kernel of the last gq_collect / gq_decode_b8 call (matching decoder: the first-tier
+ * kernel most shots went through), timed with CUDA events on the decoder's stream:
+ * {milliseconds summed over its launches, launches, shots it decoded, K = ceil(defects / 32) of its class} */
+int gq_last_kernel_profile(const gq_dec *dec, double out[4]);
 
 int gq_sync(gq_dem *dem);
 
