@@ -42,6 +42,11 @@ typedef unsigned __int128 gqw_mask;   // one bit per slot; the single host lane 
 typedef unsigned gqw_mask;
 #endif
 #define GQW_FULL 0xffffffffu
+#ifndef GQ_AP_UNROLL
+#define GQ_AP_UNROLL 2   // rows of the all-pairs pass in flight per warp
+#endif
+#define GQ_PRAGMA_STR(x) _Pragma(#x)
+#define GQ_PRAGMA_UNROLL(n) GQ_PRAGMA_STR(unroll n)
 #define GQW_BIT(k) ((gqw_mask)1 << (k))
 
 #ifdef GQ_MT_STATS
@@ -449,7 +454,7 @@ __device__ __forceinline__ int decode_shot(const Tables &T, FT &f, const u16 *de
         key[k] = 0xffffffffu;
     }
     // ---- nearest other defect of every defect: key = distance << 8 | index (diagonal = W_INF)
-#pragma unroll 2
+    GQ_PRAGMA_UNROLL(GQ_AP_UNROLL)
     for (int i = 0; i < n; ++i) {
         const uint32_t ro = (uint32_t)def[i] * N;
 #pragma unroll
