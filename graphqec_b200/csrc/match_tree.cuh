@@ -137,9 +137,12 @@ __device__ __forceinline__ int sel_slot(const TV (&arr)[K], const int slot) {
 //        unlabelled vertex, 1: outer-outer edge turns tight); an inner vertex keeps its frozen slack
 //        in the same layout with bit 31 set, which also keeps it out of the search
 //   bk = boundary event of an outer vertex: time << 10 | 3 << 8 | vertex
-// Labels in registers: 0 unlabelled, +1 outer, -1 inner, so that y = yb + vlab * D.
+// Label of a slot = the key bits it contributes: kb = vertex (unlabelled), vertex | 0x100 (outer),
+// vertex | bit 31 (inner).  With X = 4w - y_u + (D - yb[k]) the candidate time of an edge from outer u
+// is X for unlabelled and inner targets (time resp. frozen slack) and X / 2 for outer ones.
 static const unsigned EK_NONE = 0x7fffffffu;   // no pending edge event (time field all ones)
 static const unsigned EK_FROZEN = 0x80000000u;
+static const unsigned KB_OUTER = 0x100u;
 
 __device__ __forceinline__ bool ek_has(unsigned ek) { return (ek | 0x800003ffu) != 0xffffffffu; }
 __device__ __forceinline__ i32 ek_time(unsigned ek) { return (i32)((ek >> 10) & 0x1fffffu); }
@@ -150,18 +153,22 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                                           const uint32_t (&dj)[K], const i32 (&b4)[K], i32 (&yb)[K],
                                           gqw_mask freebits) {
     constexpr int cap = FT::cap;
-    unsigned ek[K], bk[K];
-    int slfrom[K], vtop[K], vlab[K];
+    unsigned ek[K], bk[K], kb[K];
+    int slfrom[K], vtop[K];
     i32 D = 0;
     int bhi = 0;
 
 #define GQT_SEL(arr, u, out) { out = __shfl_sync(GQW_FULL, sel_slot<K>(arr, (u) >> GQW_LOG), (u) & (GQW_LANES - 1)); }
+#define GQT_IS_OUTER(k_) ((kb[k_] & KB_OUTER) != 0)
+#define GQT_IS_INNER(k_) ((int)kb[k_] < 0)
 // slot k_ turns outer at clock D (yb[k_] already rebased): boundary event, key bits
 #define GQT_MAKE_OUTER(k_)                                                                      \
     {                                                                                           \
-        vlab[k_] = 1;                                                                           \
+        kb[k_] = (unsigned)(lane + GQW_LANES * (k_)) | KB_OUTER;                                \
         bk[k_] = b4[k_] < SL_INF ? (((unsigned)(b4[k_] - yb[k_]) << 10) | 0x300u | (unsigned)(lane + GQW_LANES * (k_))) : 0xffffffffu; \
     }
+// uniform scan masks: one vertex / the vertices flagged by a per-lane predicate
+#define GQT_MASK_ONE(u_) { _Pragma("unroll") for (int k_ = 0; k_ < K; ++k_) nm[k_] = (((u_) >> GQW_LOG) == k_) ? (1u << ((u_) & (GQW_LANES - 1))) : 0u; }
 // scan the row of outer vertex u_ (its dual is yb + D): offer its edges to every vertex of other nodes
 #define GQT_SCAN(u_)                                                                            \
     {                                                                                           \
@@ -169,35 +176,15 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
         const int tu_ = f.top[su_];                                                             \
         i32 yu_;                                                                                \
         GQT_SEL(yb, su_, yu_);                                                                  \
-        yu_ += D;                                                                               \
+        const i32 e0_ = -yu_;            /* D - (yb_u + D) */                                   \
         const uint32_t ro_ = (uint32_t)def[su_] * N;                                            \
         _Pragma("unroll") for (int k_ = 0; k_ < K; ++k_) {                                      \
             const i32 wt_ = (i32)dist[ro_ + dj[k_]];                                            \
-            const i32 s_ = 4 * wt_ - yu_ - (yb[k_] + vlab[k_] * D);                             \
-            const unsigned v_ = (unsigned)(lane + GQW_LANES * k_);                              \
-            const unsigned nk_ = vlab[k_] == 0 ? (((unsigned)(D + s_) << 10) | v_)              \
-                               : (vlab[k_] > 0 ? (((unsigned)(D + (s_ >> 1)) << 10) | 0x100u | v_) \
-                                               : (((unsigned)s_ << 10) | EK_FROZEN | v_));      \
-            if (wt_ != (i32)W_INF && vtop[k_] != tu_ && nk_ < ek[k_]) { ek[k_] = nk_; slfrom[k_] = su_; } \
-        }                                                                                       \
-    }
-// scan every vertex flagged in pred[]; one instance of the scan body (code size), slots walked by a
-// runtime loop over their ballots
-#define GQT_SCAN_WHERE(pred)                                                                    \
-    {                                                                                           \
-        unsigned pm_[K];                                                                        \
-        unsigned any_ = 0;                                                                      \
-        _Pragma("unroll") for (int kk_ = 0; kk_ < K; ++kk_) { pm_[kk_] = __ballot_sync(GQW_FULL, pred[kk_]); any_ |= pm_[kk_]; } \
-        if (any_) {                                                                             \
-            _Pragma("unroll 1") for (int kk_ = 0; kk_ < K; ++kk_) {                             \
-                unsigned m_ = (unsigned)sel_slot<K>(pm_, kk_);                                  \
-                _Pragma("unroll 1") while (m_) {                                                \
-                    const int b_ = __ffs(m_) - 1;                                               \
-                    m_ &= m_ - 1;                                                               \
-                    GQM_STAT(6, 1);                                                             \
-                    GQT_SCAN(GQW_LANES * kk_ + b_);                                             \
-                }                                                                               \
-            }                                                                                   \
+            const i32 x_ = 4 * wt_ + (e0_ - yb[k_]);                                            \
+            const unsigned nk_ = ((unsigned)(x_ >> ((kb[k_] >> 8) & 1u)) << 10) + kb[k_];       \
+            const bool up_ = wt_ != (i32)W_INF && vtop[k_] != tu_ && nk_ < ek[k_];              \
+            ek[k_] = up_ ? nk_ : ek[k_];                                                        \
+            slfrom[k_] = up_ ? su_ : slfrom[k_];                                                \
         }                                                                                       \
     }
 
@@ -209,7 +196,8 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
     for (int i = lane; i < FT::nb; i += GQW_LANES) f.bused[i] = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        vtop[k] = lane + GQW_LANES * k; vlab[k] = 0;
+        vtop[k] = lane + GQW_LANES * k;
+        kb[k] = (unsigned)(lane + GQW_LANES * k);
         bk[k] = 0xffffffffu;
     }
     __syncwarp();
@@ -224,23 +212,35 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
             if (f.mate[root] != -1) continue;   // became the far end of an earlier augmenting path
             // ---- phase: one alternating tree rooted at root
             D = 0;
-            bool news[K];
+            unsigned nm[K];          // warp-uniform masks of the vertices to scan next, per slot
+            bool inner_blossoms = false;   // an inner (T) top-level blossom exists in this tree
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 ek[k] = EK_NONE; slfrom[k] = -1;
-                news[k] = lane + GQW_LANES * k == root;
-                if (news[k]) { GQT_MAKE_OUTER(k); f.label[root] = L_S; }
+                if (lane + GQW_LANES * k == root) { GQT_MAKE_OUTER(k); f.label[root] = L_S; }
             }
+            GQT_MASK_ONE(root);
             __syncwarp();
             int vfree = -1;
             for (int guard = 0;; ++guard) {
-                GQT_SCAN_WHERE(news);
+                // ---- scan the rows of the vertices that just turned outer (one body, runtime loops)
+#pragma unroll 1
+                for (int kk = 0; kk < K; ++kk) {
+                    unsigned m = (unsigned)sel_slot<K>(nm, kk);
+#pragma unroll 1
+                    while (m) {
+                        const int b_ = __ffs(m) - 1;
+                        m &= m - 1;
+                        GQM_STAT(6, 1);
+                        GQT_SCAN(GQW_LANES * kk + b_);
+                    }
+                }
                 if (guard > 8 * (cap + FT::nb) + 64) return 3;
                 // ---- earliest event
                 unsigned best = 0xffffffffu;
 #pragma unroll
                 for (int k = 0; k < K; ++k) best = min(best, min(ek[k], bk[k]));
-                if (bhi) {
+                if (inner_blossoms) {
 #pragma unroll 1
                     for (int i = lane; i < bhi; i += GQW_LANES)
                         if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] == L_T)
@@ -255,7 +255,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                 int src = -1;
                 if (type < 2) GQT_SEL(slfrom, arg, src);
 #pragma unroll
-                for (int k = 0; k < K; ++k) news[k] = false;
+                for (int k = 0; k < K; ++k) nm[k] = 0u;
                 if (type == 1 && f.top[src] == f.top[arg]) {
                     GQM_STAT(1, 1);
                     // stale: the source was swallowed by the target's blossom -> recompute the best
@@ -270,7 +270,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     for (int k = 0; k < K; ++k) {
                         const i32 wt = (i32)dist[ro + dj[k]];
                         const i32 s = 4 * wt - yv - (yb[k] + D);
-                        if (vlab[k] > 0 && vtop[k] != tv && wt != (i32)W_INF)
+                        if (GQT_IS_OUTER(k) && vtop[k] != tv && wt != (i32)W_INF)
                             bb = min(bb, ((unsigned)s << 8) | (unsigned)(lane + GQW_LANES * k));
                     }
                     bb = __reduce_min_sync(GQW_FULL, bb);
@@ -303,16 +303,25 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                         if (tn >= cap) f.yb[tn - cap] += 2 * D;   // z = zb - 2D from now on
                         if (sn >= cap) f.yb[sn - cap] -= 2 * D;   // z = zb + 2D
                     }
+                    if (tn >= cap) inner_blossoms = true;
+                    bool turned[K];
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
+                        turned[k] = false;
                         if (vtop[k] == tn) {
-                            vlab[k] = -1; yb[k] += D;
+                            yb[k] += D;
                             ek[k] = ek_has(ek[k]) ? ((ek[k] - ((unsigned)D << 10)) | EK_FROZEN) : 0xffffffffu;
+                            kb[k] = (unsigned)(lane + GQW_LANES * k) | EK_FROZEN;
                         } else if (vtop[k] == sn) {
-                            yb[k] -= D; news[k] = true;
+                            yb[k] -= D; turned[k] = true;
                             if (ek_has(ek[k])) ek[k] = ((unsigned)((ek_time(ek[k]) + D) >> 1) << 10) | 0x100u | (unsigned)(lane + GQW_LANES * k);
                             GQT_MAKE_OUTER(k);
                         }
+                    }
+                    if (sn < cap) { GQT_MASK_ONE(sn); }
+                    else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) nm[k] = __ballot_sync(GQW_FULL, turned[k]);
                     }
                     __syncwarp();
                 } else if (type == 3) {
@@ -348,9 +357,10 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const int x = lane + GQW_LANES * k;
+                        bool turned = false;
                         if (x < n && f.par[vtop[k]] == b) {
-                            if (vlab[k] < 0) {
-                                news[k] = true;
+                            if (GQT_IS_INNER(k)) {
+                                turned = true;
                                 yb[k] -= 2 * D;
                                 ek[k] = ek_has(ek[k]) ? (((unsigned)(D + (ek_time(ek[k]) >> 1)) << 10) | 0x100u | (unsigned)x) : EK_NONE;
                                 GQT_MAKE_OUTER(k);
@@ -358,12 +368,14 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                             vtop[k] = b;
                             f.top[x] = (i16)b;
                         }
+                        nm[k] = __ballot_sync(GQW_FULL, turned);
                     }
                     __syncwarp();
                 } else {
                     GQM_STAT(7, 1);
-                    // ---- an inner blossom's dual reached zero: expand
+                    // ---- an inner blossom's dual reached zero: expand (its children may be inner blossoms)
                     const int b = cap + arg;
+                    inner_blossoms = true;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const int x = lane + GQW_LANES * k;
@@ -389,18 +401,20 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const int x = lane + GQW_LANES * k;
-                        if (x < n && vlab[k] < 0) {
+                        bool turned = false;
+                        if (x < n && GQT_IS_INNER(k)) {
                             const int nl = f.label[vtop[k]];
                             if (nl == L_S) {
-                                news[k] = true; yb[k] -= 2 * D;
+                                turned = true; yb[k] -= 2 * D;
                                 ek[k] = ek_has(ek[k]) ? (((unsigned)(D + (ek_time(ek[k]) >> 1)) << 10) | 0x100u | (unsigned)x) : EK_NONE;
                                 GQT_MAKE_OUTER(k);
                             } else if (nl == L_NONE) {
                                 yb[k] -= D;
                                 ek[k] = ek_has(ek[k]) ? (((unsigned)(D + ek_time(ek[k])) << 10) | (unsigned)x) : EK_NONE;
-                                vlab[k] = 0;
+                                kb[k] = (unsigned)x;
                             }
                         }
+                        nm[k] = __ballot_sync(GQW_FULL, turned);
                     }
                 }
             }
@@ -417,9 +431,9 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int x = lane + GQW_LANES * k;
-                if (vlab[k] != 0) {
-                    yb[k] += vlab[k] * D;
-                    vlab[k] = 0; bk[k] = 0xffffffffu;
+                if (kb[k] != (unsigned)x) {
+                    yb[k] += GQT_IS_OUTER(k) ? D : -D;
+                    kb[k] = (unsigned)x; bk[k] = 0xffffffffu;
                     f.label[vtop[k]] = L_NONE;
                 }
                 if (x == root || x == vfree) freebits &= ~GQW_BIT(k);
@@ -429,9 +443,11 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
     }
     return 0;
 #undef GQT_SEL
+#undef GQT_IS_OUTER
+#undef GQT_IS_INNER
 #undef GQT_MAKE_OUTER
+#undef GQT_MASK_ONE
 #undef GQT_SCAN
-#undef GQT_SCAN_WHERE
 }
 
 // ---- one shot: defects def[0..n) (32*(K-1) < n <= 32*K on the device) -> prediction mask, weight.
