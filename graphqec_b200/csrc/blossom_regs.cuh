@@ -150,13 +150,13 @@ __device__ GQ_SURGERY_INLINE void augment(FT &f, int u, int v) {
     for (;;) {
         int x = f.top[a];
         int m = f.mate[f.base[x]];
-        rebase(f, x, a);
+        if (x >= f.cap) rebase(f, x, a);   // plain vertices need no rebasing (the common case)
         f.mate[a] = (i16)nm;
         if (nm >= 0) f.mate[nm] = (i16)a;
         if (m < 0) break;
         int t = f.top[m];
         int tpu = f.pu[t], tpv = f.pv[t];
-        rebase(f, t, tpv);
+        if (t >= f.cap) rebase(f, t, tpv);
         nm = tpv; a = tpu;
     }
 }
@@ -170,14 +170,14 @@ __device__ GQ_SURGERY_INLINE void augment_half(FT &f, int u, int nm0) {
     for (;;) {
         int x = f.top[a];
         int m = f.mate[f.base[x]];
-        rebase(f, x, a);
+        if (x >= f.cap) rebase(f, x, a);   // plain vertices need no rebasing (the common case)
         f.mate[a] = (i16)nm;
         if (!first) f.mate[nm] = (i16)a;
         first = 0;
         if (m < 0) break;
         int t = f.top[m];
         int tpu = f.pu[t], tpv = f.pv[t];
-        rebase(f, t, tpv);
+        if (t >= f.cap) rebase(f, t, tpv);
         nm = tpv; a = tpu;
     }
 }

@@ -224,15 +224,20 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
             int vfree = -1;
             for (int guard = 0;; ++guard) {
                 // ---- scan the rows of the vertices that just turned outer (one body, runtime loops)
+                unsigned nm_any = 0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) nm_any |= nm[k];
+                if (nm_any) {
 #pragma unroll 1
-                for (int kk = 0; kk < K; ++kk) {
-                    unsigned m = (unsigned)sel_slot<K>(nm, kk);
+                    for (int kk = 0; kk < K; ++kk) {
+                        unsigned m = (unsigned)sel_slot<K>(nm, kk);
 #pragma unroll 1
-                    while (m) {
-                        const int b_ = __ffs(m) - 1;
-                        m &= m - 1;
-                        GQM_STAT(6, 1);
-                        GQT_SCAN(GQW_LANES * kk + b_);
+                        while (m) {
+                            const int b_ = __ffs(m) - 1;
+                            m &= m - 1;
+                            GQM_STAT(6, 1);
+                            GQT_SCAN(GQW_LANES * kk + b_);
+                        }
                     }
                 }
                 if (guard > 8 * (cap + FT::nb) + 64) return 3;
@@ -292,7 +297,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                         // the node is free (m == -1, a plain vertex) or sits on the boundary
                         // (m == -2): u takes it over; a boundary match is simply released
                         GQM_STAT(4, 1);
-                        if (lane == 0) { gqr::rebase(f, tn, v); gqr::augment(f, u, v); }
+                        if (lane == 0) { if (tn >= cap) gqr::rebase(f, tn, v); gqr::augment(f, u, v); }
                         if (m == -1) vfree = v;
                         break;
                     }
