@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--shots", type=int, default=1 << 22, help="shots per step per GPU")
-    ap.add_argument("--e2e-shots", type=int, default=1 << 20)
+    ap.add_argument("--e2e-shots", type=int, default=0, help="shots per e2e step per GPU (default: --shots)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -236,7 +236,8 @@ def main():
     value = tot_shots / dt
 
     # ---- e2e: host buffers through gq_decode_b8 (the sinter plug-in seam), copies inside the timing
-    ne = max(tile, args.e2e_shots - args.e2e_shots % tile)
+    e2e_shots = args.e2e_shots or args.shots
+    ne = max(tile, e2e_shots - e2e_shots % tile)
     dets_dev, obs_dev = demh.sample(SEED + 1, 0, ne)
     db = (dem.num_detectors + 7) // 8
     host_dets = torch.empty((ne, db), dtype=torch.uint8, pin_memory=True)

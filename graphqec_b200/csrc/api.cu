@@ -71,6 +71,10 @@ extern "C" void gq_decoder_destroy(gq_dec *dec) {
     else if (dec->kind == GQ_DECODER_BP_MINSUM) gq_bp_destroy(dec);
     cudaFree(dec->d_dets); cudaFree(dec->d_obs); cudaFree(dec->d_pred); cudaFree(dec->d_count);
     cudaFree(dec->d_b8);
+    if (dec->copy_stream) {
+        cudaStreamDestroy(dec->copy_stream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(dec->ev_copied[i]); cudaEventDestroy(dec->ev_consumed[i]); }
+    }
     delete dec;
 }
 
@@ -133,30 +137,60 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
     gq_dem *dem = dec->dem;
     GQ_CUDA(cudaSetDevice(dem->device));
     const size_t db = (dem->D + 7) / 8, ob = std::max<size_t>(1, (dem->O + 7) / 8);
-    const uint64_t chunk = 1ull << 20;
-    cudaEvent_t e0, e1, e2, e3;
+    // Software pipeline over chunks: the H2D copy of chunk c+1 runs on a second stream while chunk c is
+    // decoded (the decoder synchronises its own stream with the host; the copy stream keeps going).
+    // Two raw-input buffers; a buffer is free again once its rows were re-strided into d_dets.
+    // (chunks of 2^20 shots keep the decoder's per-slice launch overhead small; calls too short for two
+    // of those are cut into 2^18-shot chunks so that their copy still overlaps)
+    const uint64_t chunk = nshots >= (1ull << 21) ? (1ull << 20) : (nshots > (1ull << 19) ? (1ull << 18) : (1ull << 20));
+    const uint64_t nchunks = (nshots + chunk - 1) / chunk;
+    if (!dec->copy_stream) {
+        GQ_CUDA(cudaStreamCreateWithFlags(&dec->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            GQ_CUDA(cudaEventCreateWithFlags(&dec->ev_copied[i], cudaEventDisableTiming));
+            GQ_CUDA(cudaEventCreateWithFlags(&dec->ev_consumed[i], cudaEventDisableTiming));
+        }
+    }
+    cudaEvent_t e0, e1, e2, e3, ea, ez;
     GQ_CUDA(cudaEventCreate(&e0)); GQ_CUDA(cudaEventCreate(&e1));
     GQ_CUDA(cudaEventCreate(&e2)); GQ_CUDA(cudaEventCreate(&e3));
-    double t_h2d = 0, t_dec = 0, t_d2h = 0;
+    GQ_CUDA(cudaEventCreate(&ea)); GQ_CUDA(cudaEventCreate(&ez));
+    double t_wait = 0, t_dec = 0, t_d2h = 0;
     int launches = 0;
     memset(dec->kprof, 0, sizeof(dec->kprof));
     int rc = ensure_scratch(dec, std::min(chunk, nshots));
     if (rc) return rc;
-    if (dec->b8_bytes < chunk * (db + ob)) {
+    const size_t need = chunk * (2 * db + ob);
+    if (dec->b8_bytes < need) {
         cudaFree(dec->d_b8);
         dec->d_b8 = nullptr; dec->b8_bytes = 0;
-        GQ_CUDA(cudaMalloc((void **)&dec->d_b8, chunk * (db + ob)));
-        dec->b8_bytes = chunk * (db + ob);
+        GQ_CUDA(cudaMalloc((void **)&dec->d_b8, need));
+        dec->b8_bytes = need;
     }
-    uint8_t *d_in = dec->d_b8, *d_out = dec->d_b8 + chunk * db;
-    for (uint64_t s0 = 0; s0 < nshots; s0 += chunk) {
-        uint64_t ns = std::min(chunk, nshots - s0);
+    uint8_t *d_in[2] = {dec->d_b8, dec->d_b8 + chunk * db};
+    uint8_t *d_out = dec->d_b8 + 2 * chunk * db;
+    auto issue_copy = [&](uint64_t c) -> int {
+        const uint64_t s0 = c * chunk, ns = std::min(chunk, nshots - s0);
+        const int buf = (int)(c & 1);
+        if (c >= 2) GQ_CUDA(cudaStreamWaitEvent(dec->copy_stream, dec->ev_consumed[buf], 0));
+        GQ_CUDA(cudaMemcpyAsync(d_in[buf], dets_b8 + s0 * db, ns * db, cudaMemcpyHostToDevice, dec->copy_stream));
+        GQ_CUDA(cudaEventRecord(dec->ev_copied[buf], dec->copy_stream));
+        return GQ_OK;
+    };
+    GQ_CUDA(cudaEventRecord(ea, dem->stream));
+    rc = issue_copy(0);
+    if (rc) return rc;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const uint64_t s0 = c * chunk, ns = std::min(chunk, nshots - s0);
+        const int buf = (int)(c & 1);
+        if (c + 1 < nchunks) { rc = issue_copy(c + 1); if (rc) return rc; }
         GQ_CUDA(cudaEventRecord(e0, dem->stream));
-        // one contiguous copy of the b8 rows, re-strided to 4-byte aligned rows on the device
-        GQ_CUDA(cudaMemcpyAsync(d_in, dets_b8 + s0 * db, ns * db, cudaMemcpyHostToDevice, dem->stream));
-        b8_to_sm_kernel<<<dem->num_sms * 8, 256, 0, dem->stream>>>(d_in, (uint32_t)db, dem->DW, ns, dec->d_dets);
+        GQ_CUDA(cudaStreamWaitEvent(dem->stream, dec->ev_copied[buf], 0));
+        // the b8 rows arrive contiguous; re-stride them to 4-byte aligned rows on the device
+        b8_to_sm_kernel<<<dem->num_sms * 8, 256, 0, dem->stream>>>(d_in[buf], (uint32_t)db, dem->DW, ns, dec->d_dets);
         GQ_CUDA(cudaGetLastError());
         ++launches;
+        GQ_CUDA(cudaEventRecord(dec->ev_consumed[buf], dem->stream));
         GQ_CUDA(cudaEventRecord(e1, dem->stream));
         rc = decode_dispatch(dec, dec->d_dets, ns, dec->d_pred, nullptr, nullptr, nullptr, &launches);
         if (rc) return rc;
@@ -168,13 +202,19 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
         GQ_CUDA(cudaEventRecord(e3, dem->stream));
         GQ_CUDA(cudaStreamSynchronize(dem->stream));
         float ms;
-        cudaEventElapsedTime(&ms, e0, e1); t_h2d += ms;
+        cudaEventElapsedTime(&ms, e0, e1); t_wait += ms;   // exposed (not overlapped) copy time + re-stride
         cudaEventElapsedTime(&ms, e1, e2); t_dec += ms;
         cudaEventElapsedTime(&ms, e2, e3); t_d2h += ms;
     }
+    GQ_CUDA(cudaEventRecord(ez, dem->stream));
+    GQ_CUDA(cudaStreamSynchronize(dem->stream));
+    GQ_CUDA(cudaStreamSynchronize(dec->copy_stream));
+    float total = 0;
+    cudaEventElapsedTime(&total, ea, ez);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    cudaEventDestroy(ea); cudaEventDestroy(ez);
     double *t = dec->timing;
-    t[0] = 0; t[1] = t_dec; t[2] = 0; t[3] = t_h2d + t_dec + t_d2h; t[4] = t_h2d; t[5] = t_d2h; t[6] = launches; t[7] = 0;
+    t[0] = 0; t[1] = t_dec; t[2] = 0; t[3] = total; t[4] = t_wait; t[5] = t_d2h; t[6] = launches; t[7] = 0;
     return GQ_OK;
 }
 

@@ -69,6 +69,8 @@ struct gq_dec {
     double timing[8] = {0};
     double kprof[4] = {0};             // dominant first-tier kernel of the last call: {ms, launches, shots, K}
     cudaEvent_t kev0 = nullptr, kev1 = nullptr;
+    cudaStream_t side_streams[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // first tier: the smaller classes' kernels
+    cudaEvent_t side_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // ---- matching
     uint32_t num_edges = 0, num_boundary = 0;
     std::vector<uint32_t> eu, ev, ew;
@@ -101,6 +103,8 @@ struct gq_dec {
     uint64_t scratch_shots = 0;
     uint64_t *d_count = nullptr;
     uint8_t *d_b8 = nullptr;
+    cudaStream_t copy_stream = nullptr;            // gq_decode_b8: H2D of the next chunk overlaps the decode
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     uint64_t b8_bytes = 0;
 };
 

@@ -604,6 +604,10 @@ int gq_matching_create(gq_dec *dec) {
     GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<5>))));
     GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<6>))));
     GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << 20) + 16) * 4));
+    for (int i = 0; i < 5; ++i) {
+        GQ_CUDA(cudaStreamCreateWithFlags(&dec->side_streams[i], cudaStreamNonBlocking));
+        GQ_CUDA(cudaEventCreateWithFlags(&dec->side_done[i], cudaEventDisableTiming));
+    }
     GQ_CUDA(cudaEventCreate(&dec->kev0));
     GQ_CUDA(cudaEventCreate(&dec->kev1));
     dec->overflow_cap = 1u << 20;
@@ -622,6 +626,10 @@ void gq_matching_destroy(gq_dec *dec) {
     cudaFree(dec->d_dist); cudaFree(dec->d_pobs); cudaFree(dec->d_next);
     cudaFree(dec->d_adj_ptr); cudaFree(dec->d_adj_node); cudaFree(dec->d_adj_edge);
     cudaFree(dec->d_ws_fast); cudaFree(dec->d_ws_big); cudaFree(dec->d_overflow); cudaFree(dec->d_lists);
+    for (int i = 0; i < 5; ++i) {
+        if (dec->side_streams[i]) cudaStreamDestroy(dec->side_streams[i]);
+        if (dec->side_done[i]) cudaEventDestroy(dec->side_done[i]);
+    }
     if (dec->kev0) cudaEventDestroy(dec->kev0);
     if (dec->kev1) cudaEventDestroy(dec->kev1);
 }
@@ -677,24 +685,33 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
             std::sort(order, order + MT_CLASSES, [&](int x, int y) { return counts[x] > counts[y]; });
             int dom = 0;   // the class most shots of this slice fall in: its kernel is the one bench.py's roofline names
             for (int c = 1; c < MT_CLASSES; ++c) if (counts[c] > counts[dom]) dom = c;
+            // the biggest class runs on the decoder's stream, the others on side streams: they start as soon
+            // as the big kernel's persistent blocks begin to retire, so the tails of the launches overlap
+            // (the host synchronised after classify_kernel, so nothing earlier is still in flight)
+            int nside = 0;
             for (int oi = 0; oi < MT_CLASSES; ++oi) {
                 const int c = order[oi];
                 if (counts[c] == 0) continue;
-                if (c == dom) GQ_CUDA(cudaEventRecord(dec->kev0, dem->stream));
+                cudaStream_t st = (oi == 0 || !dec->side_streams[0]) ? dem->stream : dec->side_streams[nside++];
+                if (c == dom) GQ_CUDA(cudaEventRecord(dec->kev0, st));
                 b.list = d_lists + (size_t)c * slice; b.nitems = counts[c];
                 const int per_sm = c < 4 ? GQ_MT_PER_SM : 2;
                 const int blocks = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * per_sm);
                 switch (c) {
-                case 0: match_tree_kernel<1><<<blocks, 256, 8 * sizeof(MtWarpMem<1>), dem->stream>>>(b); break;
-                case 1: match_tree_kernel<2><<<blocks, 256, 8 * sizeof(MtWarpMem<2>), dem->stream>>>(b); break;
-                case 2: match_tree_kernel<3><<<blocks, 256, 8 * sizeof(MtWarpMem<3>), dem->stream>>>(b); break;
-                case 3: match_tree_kernel<4><<<blocks, 256, 8 * sizeof(MtWarpMem<4>), dem->stream>>>(b); break;
-                case 4: match_tree_kernel<5><<<blocks, 256, 8 * sizeof(MtWarpMem<5>), dem->stream>>>(b); break;
-                default: match_tree_kernel<6><<<blocks, 256, 8 * sizeof(MtWarpMem<6>), dem->stream>>>(b); break;
+                case 0: match_tree_kernel<1><<<blocks, 256, 8 * sizeof(MtWarpMem<1>), st>>>(b); break;
+                case 1: match_tree_kernel<2><<<blocks, 256, 8 * sizeof(MtWarpMem<2>), st>>>(b); break;
+                case 2: match_tree_kernel<3><<<blocks, 256, 8 * sizeof(MtWarpMem<3>), st>>>(b); break;
+                case 3: match_tree_kernel<4><<<blocks, 256, 8 * sizeof(MtWarpMem<4>), st>>>(b); break;
+                case 4: match_tree_kernel<5><<<blocks, 256, 8 * sizeof(MtWarpMem<5>), st>>>(b); break;
+                default: match_tree_kernel<6><<<blocks, 256, 8 * sizeof(MtWarpMem<6>), st>>>(b); break;
                 }
                 GQ_CUDA(cudaGetLastError());
                 ++*launches;
-                if (c == dom) GQ_CUDA(cudaEventRecord(dec->kev1, dem->stream));
+                if (c == dom) GQ_CUDA(cudaEventRecord(dec->kev1, st));
+                if (st != dem->stream) {
+                    GQ_CUDA(cudaEventRecord(dec->side_done[nside - 1], st));
+                    GQ_CUDA(cudaStreamWaitEvent(dem->stream, dec->side_done[nside - 1], 0));
+                }
             }
             uint32_t ovf[2];
             GQ_CUDA(cudaMemcpyAsync(ovf, ovf_buf[cur], 8, cudaMemcpyDeviceToHost, dem->stream));
