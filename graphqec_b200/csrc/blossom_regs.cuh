@@ -92,14 +92,20 @@ struct StaticForest {
 };
 
 // ---------------------------------------------------------------- lane 0 forest surgery
-// inlined by default (measured: out-of-line calls cost more in spills than they save in fetch);
-// -DGQ_SURGERY_INLINE=__noinline__ keeps them out of the event loop for experiments
+// augment / augment_half run once per phase and stay inline (out of line they cost more in spills around
+// the call than they save).  rebase, shrink and expand_relabel only run when a blossom is involved (about
+// twice per shot at the north star) but are large -- rebase alone was inlined five times: out of line
+// they take ~1 k instructions out of the event loop's footprint, which matters because the kernels sit at
+// the edge of the instruction cache (sm__icc_request_hit_rate, profiles/).
 #ifndef GQ_SURGERY_INLINE
 #define GQ_SURGERY_INLINE __forceinline__
 #endif
+#ifndef GQ_RARE_INLINE
+#define GQ_RARE_INLINE __noinline__
+#endif
 // (FT = Forest or StaticForest<CAP>)
 template <class FT>
-__device__ GQ_SURGERY_INLINE void rebase(FT &f, int x0, int a0) {
+__device__ GQ_RARE_INLINE void rebase(FT &f, int x0, int a0) {
     const int cap = f.cap;
     int sp = 0;
     f.stk[sp++] = (i16)x0; f.stk[sp++] = (i16)a0;
@@ -193,7 +199,7 @@ __device__ __forceinline__ int parent_S(FT &f, int x, int *tnode) {
 
 // mark[] must be zero on entry
 template <class FT>
-__device__ GQ_SURGERY_INLINE int shrink(FT &f, int u, int v) {
+__device__ GQ_RARE_INLINE int shrink(FT &f, int u, int v) {
     const int cap = f.cap, nb = f.nb;
     int xu = f.top[u], xv = f.top[v];
 #pragma unroll 1
@@ -253,7 +259,7 @@ __device__ GQ_SURGERY_INLINE int shrink(FT &f, int u, int v) {
 
 // relabel the children of T blossom b (top[] of its vertices already points at them)
 template <class FT>
-__device__ GQ_SURGERY_INLINE void expand_relabel(FT &f, int b) {
+__device__ GQ_RARE_INLINE void expand_relabel(FT &f, int b) {
     const int cap = f.cap;
     const int fst = f.first[b - cap];
     const int c = f.top[f.pv[b]];

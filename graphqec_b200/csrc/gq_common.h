@@ -79,6 +79,7 @@ struct gq_dec {
     uint32_t fast_cap = 0, max_cap = 0, max_dist = 0;
     uint16_t *d_dist = nullptr;        // [D][D+1]
     uint8_t *d_pobs = nullptr;         // [D][D+1] observable mask of the shortest path
+    uint32_t *d_nbr = nullptr;         // [D+2][NBR_LEN] nearest detectors of each detector (distance << 16 | detector)
     uint16_t *d_next = nullptr;        // [D][D+1] next node on the shortest path (0xFFFF = boundary hop)
     uint32_t *d_adj_ptr = nullptr;     // [D+1]   adjacency for corrections
     uint32_t *d_adj_node = nullptr;    // neighbour (D = boundary)
@@ -88,6 +89,8 @@ struct gq_dec {
     size_t ws_fast_bytes = 0, ws_big_bytes = 0;
     int nwarps_fast = 0, nwarps_big = 0;
     uint32_t *d_overflow = nullptr;    // [1 + capacity] overflow shot list
+    void *d_recs = nullptr;            // first tier: hand-off records between the start and the solve kernels
+    size_t recs_bytes = 0;
     uint32_t *d_lists = nullptr;       // first tier: [16] class counts, then one shot list per class
     uint32_t overflow_cap = 0;
     // ---- BP

@@ -2,7 +2,9 @@
 //
 // decode_shot<K>() takes the defect list of one shot (32*(K-1) < n <= 32*K defects, ascending
 // detector index) and returns the exact minimum-weight matching's observable prediction:
-//   1. all-pairs pass over the L2-resident distance table: nearest other defect of every defect;
+//   1. nearest other defect of every defect: the 16 nearest detectors of its detector (a static sorted
+//      list) are tested against the syndrome bits in shared memory; the few defects with no fired
+//      detector among them take a full row of the L2-resident distance table instead;
 //   2. dual start y(v) = min(nearest/2, boundary distance): a vertex whose boundary is at least as
 //      close as half its nearest defect starts matched to the boundary; mutual nearest neighbours
 //      are tight and start matched to each other (one lane-parallel step, no sequential greedy);
@@ -70,12 +72,18 @@ struct Tables {
     const u16 *dist;       // [N][N]: row/column D = the boundary, D + 1 = nothing (all W_INF); diagonal = W_INF
     const uint8_t *pobs;   // [N][N] observable mask of the shortest path
     uint32_t N, D;         // N = D + 2
+    const uint32_t *nbr;   // [N][NBR_LEN]: the nearest other detectors of each detector, ascending distance,
+                           // entry = distance << 16 | detector; padding = 0xffff << 16 | 32 * DW (a detector
+                           // index whose syndrome word is the always-zero word behind the row)
 };
+
+static constexpr int NBR_LEN = 16;
+static constexpr int SYN_WORDS = 256;   // syndrome rows up to this many words are mirrored in shared memory
 
 // ---- defect list of one bit-packed syndrome row (ascending detector index); returns the count,
 // stores the first cap entries
 __device__ __forceinline__ int extract_defects(const uint32_t *row, uint32_t DW, uint32_t D, int lane,
-                                               u16 *def, int cap) {
+                                               u16 *def, int cap, uint32_t *synw = nullptr, u16 *spre = nullptr) {
     int n0 = 0;
     for (uint32_t w0 = 0; w0 < DW; w0 += GQW_LANES) {
         const uint32_t wi = w0 + lane;
@@ -90,6 +98,7 @@ __device__ __forceinline__ int extract_defects(const uint32_t *row, uint32_t DW,
         }
         const int tot = __shfl_sync(GQW_FULL, pre, GQW_LANES - 1);
         int pos = n0 + pre - cnt;
+        if (synw && wi <= DW) { synw[wi] = word; spre[wi] = (u16)pos; }   // word DW = the zero word padding points at
         while (word) {
             int b = __ffs(word) - 1;
             word &= word - 1;
@@ -98,10 +107,10 @@ __device__ __forceinline__ int extract_defects(const uint32_t *row, uint32_t DW,
         }
         n0 += tot;
     }
+    if (synw && (DW % GQW_LANES) == 0 && lane == 0) { synw[DW] = 0u; spre[DW] = (u16)n0; }
     __syncwarp();
     return n0;
 }
-
 
 // arr[slot] for a warp-uniform slot, written as a select tree on the bits of slot: a chain of
 // "slot == k" selects gets folded back into a dynamically indexed (local-memory) array by the compiler
@@ -455,62 +464,125 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
 #undef GQT_SCAN
 }
 
-// ---- one shot: defects def[0..n) (32*(K-1) < n <= 32*K on the device) -> prediction mask, weight.
-// Returns the solver's code (0 ok).
-template <int K, class FT>
-__device__ __forceinline__ int decode_shot(const Tables &T, FT &f, const u16 *def, const int n,
-                                           const int lane, const bool want_weight, uint32_t *pm_out, int *wt_out) {
+// ---- dual start of one shot (part A): nearest other defect of every defect, y(v) = min(nearest / 2,
+// boundary), boundary matches and mutual-nearest-neighbour matches.
+// In: defects def[0..n) (shared), synw / spre (nullable): the shot's syndrome words and the number of
+// defects before each word (shared); xch: shared scratch of n int16.  Out, per slot of this lane: yb[] =
+// dual (quadrupled units, even), m0[] = initial mate (-1 free, -2 boundary, partner index; -3 for padding).
+template <int K>
+__device__ __forceinline__ void dual_start(const Tables &T, i16 *xch, const u16 *def, const int n, const int lane,
+                                           const uint32_t *synw, const u16 *spre, i32 (&yb)[K], int (&m0)[K]) {
     const u16 *__restrict__ dist = T.dist;
     const uint32_t N = T.N;
     const uint32_t bro = T.D * N;
     uint32_t dj[K];
-    i32 b4[K], yb[K];
     unsigned key[K];
+    bool miss[K];
+    // ---- nearest other defect of every defect: key = distance << 8 | index.
+    // Lane-parallel: test the NBR_LEN nearest detectors of each own defect against the syndrome bits
+    // (descending, so the nearest hit is the one that sticks); any hit is the true nearest defect because
+    // the list is a complete prefix of the detector's distance order.
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int v = lane + GQW_LANES * k;
         dj[k] = v < n ? def[v] : T.D + 1;     // padding slots read the "nothing" column: all infinite
-        const uint32_t bb = dist[bro + dj[k]];
-        b4[k] = bb == (uint32_t)W_INF ? SL_INF : 4 * (i32)bb;
         key[k] = 0xffffffffu;
-    }
-    // ---- nearest other defect of every defect: key = distance << 8 | index (diagonal = W_INF)
-    GQ_PRAGMA_UNROLL(GQ_AP_UNROLL)
-    for (int i = 0; i < n; ++i) {
-        const uint32_t ro = (uint32_t)def[i] * N;
+        miss[k] = v < n;
+        if (synw != nullptr) {
+            const uint4 *L = reinterpret_cast<const uint4 *>(T.nbr + (size_t)dj[k] * NBR_LEN);
+            uint32_t hit = 0xffffffffu;
+#pragma unroll 1   // rolled on purpose: the kernels are instruction-fetch sensitive
+            for (int c = NBR_LEN / 4 - 1; c >= 0; --c) {
+                const uint4 e = L[c];
+                const uint32_t ent[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
-        for (int k = 0; k < K; ++k) key[k] = min(key[k], (unsigned)dist[ro + dj[k]] * 256u + (unsigned)i);
+                for (int q = 3; q >= 0; --q) {
+                    const uint32_t det = ent[q] & 0xffffu;
+                    hit = ((synw[det >> 5] >> (det & 31)) & 1u) ? ent[q] : hit;
+                }
+            }
+            if (hit != 0xffffffffu) {
+                const uint32_t det = hit & 0xffffu;
+                const uint32_t rank = (uint32_t)spre[det >> 5] + (uint32_t)__popc(synw[det >> 5] & ((1u << (det & 31)) - 1u));
+                key[k] = ((hit >> 16) << 8) | rank;
+                miss[k] = false;
+            }
+        }
+    }
+    // the rest (no fired detector among the listed ones; every defect when the syndrome is not mirrored):
+    // one row of the distance table per defect, all lanes gather, the minimum goes to its owner
+    {
+        unsigned mm[K];
+        unsigned any = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { mm[k] = __ballot_sync(GQW_FULL, miss[k]); any |= mm[k]; }
+        if (any) {
+#pragma unroll 1
+            for (int kk = 0; kk < K; ++kk) {
+                unsigned m = (unsigned)sel_slot<K>(mm, kk);
+#pragma unroll 1
+                while (m) {
+                    const int i = GQW_LANES * kk + __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t ro = (uint32_t)def[i] * N;
+                    unsigned best = 0xffffffffu;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) best = min(best, (unsigned)dist[ro + dj[k]] * 256u + (unsigned)(lane + GQW_LANES * k));
+                    best = __reduce_min_sync(GQW_FULL, best);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) if (lane + GQW_LANES * k == i) key[k] = best;
+                }
+            }
+        }
     }
     // ---- dual start, boundary matches, mutual nearest neighbours
-    gqw_mask freebits = 0;
     bool onb[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int v = lane + GQW_LANES * k;
+        const uint32_t bb = dist[bro + dj[k]];
+        const i32 b4 = bb == (uint32_t)W_INF ? SL_INF : 4 * (i32)bb;
         const uint32_t wmin = key[k] >> 8;
         const i32 y2 = wmin >= (uint32_t)W_INF ? SL_INF : 2 * (i32)wmin;
-        onb[k] = b4[k] < SL_INF && b4[k] <= y2;
-        yb[k] = onb[k] ? b4[k] : (y2 < SL_INF ? y2 : 0);
-        if (v < n) f.stk[v] = (i16)((onb[k] || y2 == SL_INF) ? -1 : (int)(key[k] & 0xff));
+        onb[k] = b4 < SL_INF && b4 <= y2;
+        yb[k] = onb[k] ? b4 : (y2 < SL_INF ? y2 : 0);
+        if (v < n) xch[v] = (i16)((onb[k] || y2 == SL_INF) ? -1 : (int)(key[k] & 0xff));
     }
     __syncwarp();
-    int m0[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int v = lane + GQW_LANES * k;
         m0[k] = -3;
         if (v < n) {
-            const int u = f.stk[v];
+            const int u = xch[v];
             int m = onb[k] ? -2 : -1;
-            if (u >= 0 && f.stk[u] == v) m = u;
+            if (u >= 0 && xch[u] == v) m = u;
             m0[k] = m;
-            if (m == -1) freebits |= GQW_BIT(k);
         }
     }
     __syncwarp();
+}
+
+// ---- solve and predict (part B).  In: defects def[0..n) (shared), f.mate[0..n) = the initial matching,
+// yb[] = the lane's duals.  Out: prediction mask, weight, f.mate[] = the minimum-weight matching.
+// Returns the solver's code (0 ok).
+template <int K, class FT>
+__device__ __forceinline__ int solve_predict(const Tables &T, FT &f, const u16 *def, const int n, const int lane,
+                                             const bool want_weight, i32 (&yb)[K], uint32_t *pm_out, int *wt_out) {
+    const u16 *__restrict__ dist = T.dist;
+    const uint32_t N = T.N;
+    const uint32_t bro = T.D * N;
+    uint32_t dj[K];
+    i32 b4[K];
+    gqw_mask freebits = 0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) if (m0[k] != -3) f.mate[lane + GQW_LANES * k] = (i16)m0[k];
-    __syncwarp();
+    for (int k = 0; k < K; ++k) {
+        const int v = lane + GQW_LANES * k;
+        dj[k] = v < n ? def[v] : T.D + 1;
+        const uint32_t bb = dist[bro + dj[k]];
+        b4[k] = bb == (uint32_t)W_INF ? SL_INF : 4 * (i32)bb;
+        if (v < n && f.mate[v] == -1) freebits |= GQW_BIT(k);
+    }
 #ifdef GQ_MT_STATS
     {
         int nf = 0;
@@ -556,6 +628,20 @@ __device__ __forceinline__ int decode_shot(const Tables &T, FT &f, const u16 *de
     *pm_out = pm;
     *wt_out = wt;
     return rc;
+}
+
+// ---- both parts in one call (host simulation and the fused use)
+template <int K, class FT>
+__device__ __forceinline__ int decode_shot(const Tables &T, FT &f, const u16 *def, const int n,
+                                           const int lane, const bool want_weight, uint32_t *pm_out, int *wt_out,
+                                           const uint32_t *synw = nullptr, const u16 *spre = nullptr) {
+    i32 yb[K];
+    int m0[K];
+    dual_start<K>(T, f.stk, def, n, lane, synw, spre, yb, m0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) if (m0[k] != -3) f.mate[lane + GQW_LANES * k] = (i16)m0[k];
+    __syncwarp();
+    return solve_predict<K>(T, f, def, n, lane, want_weight, yb, pm_out, wt_out);
 }
 
 }  // namespace gqt

@@ -46,6 +46,7 @@ struct MatchArgs {
     const uint16_t *dist;
     const uint8_t *pobs;
     const uint16_t *next;
+    const uint32_t *nbr;      // [N][gqt::NBR_LEN] nearest detectors of each detector (match_tree.cuh)
     const uint32_t *adj_ptr, *adj_node, *adj_edge;
     char *ws;
     size_t ws_stride;
@@ -317,6 +318,10 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
 #ifndef GQ_MT_PER_SM
 #define GQ_MT_PER_SM 4
 #endif
+#ifndef GQ_SIDE_STREAMS
+#define GQ_SIDE_STREAMS 0   // 1: the smaller classes' kernels run on side streams (overlapping tails, but co-resident
+                            // kernels share the instruction cache: measured slower once start/solve were split)
+#endif
 static constexpr int MT_CLASSES = 6;     // K = 1 .. 6
 static constexpr int MT_CAP = 32 * MT_CLASSES;
 
@@ -376,23 +381,90 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a) {
     }
 }
 
+// The first tier runs as two kernels per class so that each one's hot code fits the 32 KB L1.5
+// instruction cache (the fused kernel ran at an 80 % i-cache hit rate, 3 of 12 stall cycles per
+// instruction in no_instruction): tree_start_kernel<K> extracts the defects and computes the dual start,
+// tree_solve_kernel<K> runs the blossom phases and the prediction.  Hand-off through a per-shot record in
+// global memory (6 bytes per defect, written and read once, coalesced).
 template <int K>
-__global__ void __launch_bounds__(256, (K <= 4 ? GQ_MT_PER_SM : 2)) match_tree_kernel(MatchArgs a) {
+struct StartRecord {
+    uint16_t def[32 * K];     // detector index of every defect
+    uint16_t yh[32 * K];      // dual / 2 (duals are even, quadrupled units)
+    int16_t mate[32 * K];     // initial mate: -1 free, -2 boundary, else partner
+    uint32_t n, pad[3];
+};
+
+template <int K>
+struct StartWarpMem {
+    uint32_t synw[gqt::SYN_WORDS + 1];
+    uint16_t spre[gqt::SYN_WORDS + 2];
+    uint16_t def[32 * K];
+    int16_t xch[32 * K];
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) tree_start_kernel(MatchArgs a) {
+    extern __shared__ __align__(16) char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    StartWarpMem<K> &M = reinterpret_cast<StartWarpMem<K> *>(smem)[wib];
+    StartRecord<K> *recs = reinterpret_cast<StartRecord<K> *>(a.ws);
+    gqt::Tables T;
+    T.dist = a.dist; T.pobs = a.pobs; T.D = a.D; T.N = a.N; T.nbr = a.nbr;
+    const bool mirror = a.nbr != nullptr && a.DW <= (uint32_t)gqt::SYN_WORDS;
+    for (uint32_t item = warp; item < a.nitems; item += nwarps) {
+        const uint32_t shot = a.list[item];
+        const int n0 = gqt::extract_defects(a.dets + (size_t)shot * a.DW, a.DW, a.D, lane, M.def, 32 * K,
+                                            mirror ? M.synw : nullptr, M.spre);
+        StartRecord<K> &R = recs[item];
+        if (n0 > 32 * K || n0 <= 32 * (K - 1)) {   // the list lied about the defect count: the solver will hand it on
+            if (lane == 0) R.n = 0xffffffffu;
+            __syncwarp();
+            continue;
+        }
+        gqt::i32 yb[K];
+        int m0[K];
+        gqt::dual_start<K>(T, M.xch, M.def, n0, lane, mirror ? M.synw : nullptr, M.spre, yb, m0);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int v = lane + 32 * k;
+            if (v < n0) { R.def[v] = M.def[v]; R.yh[v] = (uint16_t)(yb[k] >> 1); R.mate[v] = (int16_t)m0[k]; }
+        }
+        if (lane == 0) R.n = (uint32_t)n0;
+        __syncwarp();
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, (K <= 4 ? GQ_MT_PER_SM : 2)) tree_solve_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     MtWarpMem<K> &M = reinterpret_cast<MtWarpMem<K> *>(smem)[wib];
+    const StartRecord<K> *recs = reinterpret_cast<const StartRecord<K> *>(a.ws);
     gqt::Tables T;
-    T.dist = a.dist; T.pobs = a.pobs; T.D = a.D; T.N = a.N;
+    T.dist = a.dist; T.pobs = a.pobs; T.D = a.D; T.N = a.N; T.nbr = a.nbr;
     const bool want_weight = a.weight_out != nullptr;
 
     for (uint32_t item = warp; item < a.nitems; item += nwarps) {
         const uint32_t shot = a.list[item];
-        const int n0 = gqt::extract_defects(a.dets + (size_t)shot * a.DW, a.DW, a.D, lane, M.def, 32 * K);
+        const StartRecord<K> &R = recs[item];
+        const uint32_t n0u = R.n;
+        int rc = 4, wt = 0, n0 = (int)n0u;
         uint32_t pm = 0;
-        int wt = 0;
-        int rc = (n0 > 32 * K || n0 <= 32 * (K - 1)) ? 4 : gqt::decode_shot<K>(T, M.F, M.def, n0, lane, want_weight, &pm, &wt);
+        if (n0u != 0xffffffffu) {
+            gqt::i32 yb[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int v = lane + 32 * k;
+                yb[k] = 0;
+                if (v < n0) { M.def[v] = R.def[v]; M.F.mate[v] = R.mate[v]; yb[k] = 2 * (gqt::i32)R.yh[v]; }
+            }
+            __syncwarp();
+            rc = gqt::solve_predict<K>(T, M.F, M.def, n0, lane, want_weight, yb, &pm, &wt);
+        } else n0 = 32 * K;
         if (rc >= 2) {
             // the solver gave up (or the list lied about the defect count): hand the shot to the ladder
             if (lane == 0) {
@@ -405,6 +477,7 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_MT_PER_SM : 2)) match_tree_k
         }
         if (rc == 0 && a.corr_out) {
             uint32_t *corr_row = a.corr_out + (size_t)shot * a.EW;
+#pragma unroll 1
             for (int i = lane; i < n0; i += 32) {
                 const int j = M.F.mate[i];
                 if (j == -2) walk_path(a, M.def[i], a.D, corr_row);
@@ -413,11 +486,43 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_MT_PER_SM : 2)) match_tree_k
         }
         if (lane == 0) {
             a.pred[(size_t)shot * a.OW] = rc == 0 ? pm : 0u;
+#pragma unroll 1
             for (uint32_t w = 1; w < a.OW; ++w) a.pred[(size_t)shot * a.OW + w] = 0u;
             if (a.weight_out) a.weight_out[shot] = rc == 0 ? wt : -1;
             if (a.flags_out) a.flags_out[shot] = (uint8_t)(rc == 0 ? 0 : 1);
         }
         __syncwarp();
+    }
+}
+
+template <int K>
+static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, int *launches) {
+    const int blocks_a = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * 6);
+    tree_start_kernel<K><<<blocks_a, 256, 8 * sizeof(StartWarpMem<K>), st>>>(b);
+    if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
+    const int per_sm = K <= 4 ? GQ_MT_PER_SM : 2;
+    const int blocks_b = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * per_sm);
+    tree_solve_kernel<K><<<blocks_b, 256, 8 * sizeof(MtWarpMem<K>), st>>>(b);
+    if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
+    *launches += 2;
+    return GQ_OK;
+}
+
+template <int K>
+static int configure_tree_class() {
+    if (cudaFuncSetAttribute(tree_start_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(StartWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
+    if (cudaFuncSetAttribute(tree_solve_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
+    return GQ_OK;
+}
+
+static size_t start_record_bytes(int c) {   // class c = K - 1
+    switch (c) {
+    case 0: return sizeof(StartRecord<1>);
+    case 1: return sizeof(StartRecord<2>);
+    case 2: return sizeof(StartRecord<3>);
+    case 3: return sizeof(StartRecord<4>);
+    case 4: return sizeof(StartRecord<5>);
+    default: return sizeof(StartRecord<6>);
     }
 }
 
@@ -557,6 +662,32 @@ int gq_matching_create(gq_dec *dec) {
     if (too_far) GQ_FAIL(GQ_E_UNSUPPORTED, "matching decoder: path lengths exceed 16 bits; lower weight_levels");
     for (uint32_t s = 0; s < N; ++s) dist[(size_t)s * NT + s] = 0xFFFFu;   // no self pairs (match_tree.cuh relies on it)
     dec->max_dist = *std::max_element(row_max.begin(), row_max.end());
+    // ---- the NBR_LEN nearest other detectors of every detector (ascending distance, ties by index) for the
+    // first tier's dual start; rows D and D + 1 and the tails are padding (see match_tree.cuh)
+    const uint32_t pad_entry = (0xFFFFu << 16) | (32u * dem->DW);
+    std::vector<uint32_t> nbr((size_t)NT * gqt::NBR_LEN, pad_entry);
+    if (32u * dem->DW <= 0xFFFFu) {
+        auto lw = [&](uint32_t s_begin, uint32_t s_end) {
+            std::vector<uint32_t> tmp;
+            for (uint32_t s = s_begin; s < s_end; ++s) {
+                tmp.clear();
+                for (uint32_t t = 0; t < D; ++t)
+                    if (t != s && dist[(size_t)s * NT + t] != 0xFFFFu) tmp.push_back(((uint32_t)dist[(size_t)s * NT + t] << 16) | t);
+                size_t keep = std::min<size_t>(gqt::NBR_LEN, tmp.size());
+                std::partial_sort(tmp.begin(), tmp.begin() + keep, tmp.end());
+                std::copy(tmp.begin(), tmp.begin() + keep, nbr.begin() + (size_t)s * gqt::NBR_LEN);
+            }
+        };
+        unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+        nt = std::min<unsigned>(nt, D);
+        std::vector<std::thread> th;
+        uint32_t per = (D + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; ++t) {
+            uint32_t b = std::min<uint32_t>(D, t * per), e = std::min<uint32_t>(D, b + per);
+            if (b < e) th.emplace_back(lw, b, e);
+        }
+        for (auto &t : th) t.join();
+    }
     // ---- capacities: expected defect count from the DEM
     std::vector<double> keep(D, 1.0);
     for (uint32_t m = 0; m < dem->M; ++m)
@@ -571,6 +702,8 @@ int gq_matching_create(gq_dec *dec) {
     // ---- upload
     GQ_CUDA(cudaMalloc((void **)&dec->d_dist, dist.size() * 2));
     GQ_CUDA(cudaMemcpy(dec->d_dist, dist.data(), dist.size() * 2, cudaMemcpyHostToDevice));
+    GQ_CUDA(cudaMalloc((void **)&dec->d_nbr, nbr.size() * 4));
+    GQ_CUDA(cudaMemcpy(dec->d_nbr, nbr.data(), nbr.size() * 4, cudaMemcpyHostToDevice));
     GQ_CUDA(cudaMalloc((void **)&dec->d_pobs, pobs.size()));
     GQ_CUDA(cudaMemcpy(dec->d_pobs, pobs.data(), pobs.size(), cudaMemcpyHostToDevice));
     if (want_next) {
@@ -597,12 +730,9 @@ int gq_matching_create(gq_dec *dec) {
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<1>))));
-    GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<2>))));
-    GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<3>))));
-    GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<4>))));
-    GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<5>))));
-    GQ_CUDA(cudaFuncSetAttribute(match_tree_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<6>))));
+    if (configure_tree_class<1>() || configure_tree_class<2>() || configure_tree_class<3>() || configure_tree_class<4>() ||
+        configure_tree_class<5>() || configure_tree_class<6>())
+        GQ_FAIL(GQ_E_CUDA, "matching decoder: cudaFuncSetAttribute failed for the first-tier kernels");
     GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << 20) + 16) * 4));
     for (int i = 0; i < 5; ++i) {
         GQ_CUDA(cudaStreamCreateWithFlags(&dec->side_streams[i], cudaStreamNonBlocking));
@@ -623,9 +753,9 @@ extern "C" void gq_debug_stats(unsigned long long *out, int reset) {
 #endif
 
 void gq_matching_destroy(gq_dec *dec) {
-    cudaFree(dec->d_dist); cudaFree(dec->d_pobs); cudaFree(dec->d_next);
+    cudaFree(dec->d_dist); cudaFree(dec->d_pobs); cudaFree(dec->d_next); cudaFree(dec->d_nbr);
     cudaFree(dec->d_adj_ptr); cudaFree(dec->d_adj_node); cudaFree(dec->d_adj_edge);
-    cudaFree(dec->d_ws_fast); cudaFree(dec->d_ws_big); cudaFree(dec->d_overflow); cudaFree(dec->d_lists);
+    cudaFree(dec->d_ws_fast); cudaFree(dec->d_ws_big); cudaFree(dec->d_overflow); cudaFree(dec->d_lists); cudaFree(dec->d_recs);
     for (int i = 0; i < 5; ++i) {
         if (dec->side_streams[i]) cudaStreamDestroy(dec->side_streams[i]);
         if (dec->side_done[i]) cudaEventDestroy(dec->side_done[i]);
@@ -644,7 +774,7 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
     a.corr_out = corr_out;
     a.D = dem->D; a.DW = dem->DW; a.OW = dem->OW; a.EW = (dec->num_edges + 31) / 32;
     a.N = dem->D + 2;
-    a.dist = dec->d_dist; a.pobs = dec->d_pobs; a.next = dec->d_next;
+    a.dist = dec->d_dist; a.pobs = dec->d_pobs; a.next = dec->d_next; a.nbr = dec->d_nbr;
     a.adj_ptr = dec->d_adj_ptr; a.adj_node = dec->d_adj_node; a.adj_edge = dec->d_adj_edge;
     // the overflow lists are bounded: process in slices so they can never overrun
     const uint64_t slice = 1ull << 20;
@@ -678,7 +808,6 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
             GQ_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(counts), cudaMemcpyDeviceToHost, dem->stream));
             GQ_CUDA(cudaStreamSynchronize(dem->stream));
             b.cap = MT_CAP;
-            b.ws = nullptr; b.ws_stride = 0;
             b.overflow = ovf_buf[cur]; b.overflow_cap = dec->overflow_cap;
             int order[MT_CLASSES];   // biggest class first
             for (int c = 0; c < MT_CLASSES; ++c) order[c] = c;
@@ -688,25 +817,33 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
             // the biggest class runs on the decoder's stream, the others on side streams: they start as soon
             // as the big kernel's persistent blocks begin to retire, so the tails of the launches overlap
             // (the host synchronised after classify_kernel, so nothing earlier is still in flight)
+            // hand-off records of the slice, one region per class
+            size_t rec_off[MT_CLASSES], rec_total = 0;
+            for (int c = 0; c < MT_CLASSES; ++c) { rec_off[c] = rec_total; rec_total += ((size_t)counts[c] * start_record_bytes(c) + 255) & ~(size_t)255; }
+            if (rec_total > dec->recs_bytes) {
+                cudaFree(dec->d_recs);
+                dec->d_recs = nullptr; dec->recs_bytes = 0;
+                GQ_CUDA(cudaMalloc(&dec->d_recs, rec_total + rec_total / 8));
+                dec->recs_bytes = rec_total + rec_total / 8;
+            }
             int nside = 0;
             for (int oi = 0; oi < MT_CLASSES; ++oi) {
                 const int c = order[oi];
                 if (counts[c] == 0) continue;
-                cudaStream_t st = (oi == 0 || !dec->side_streams[0]) ? dem->stream : dec->side_streams[nside++];
+                cudaStream_t st = (oi == 0 || !dec->side_streams[0] || !GQ_SIDE_STREAMS) ? dem->stream : dec->side_streams[nside++];
                 if (c == dom) GQ_CUDA(cudaEventRecord(dec->kev0, st));
                 b.list = d_lists + (size_t)c * slice; b.nitems = counts[c];
-                const int per_sm = c < 4 ? GQ_MT_PER_SM : 2;
-                const int blocks = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * per_sm);
+                b.ws = (char *)dec->d_recs + rec_off[c]; b.ws_stride = start_record_bytes(c);
+                int lrc;
                 switch (c) {
-                case 0: match_tree_kernel<1><<<blocks, 256, 8 * sizeof(MtWarpMem<1>), st>>>(b); break;
-                case 1: match_tree_kernel<2><<<blocks, 256, 8 * sizeof(MtWarpMem<2>), st>>>(b); break;
-                case 2: match_tree_kernel<3><<<blocks, 256, 8 * sizeof(MtWarpMem<3>), st>>>(b); break;
-                case 3: match_tree_kernel<4><<<blocks, 256, 8 * sizeof(MtWarpMem<4>), st>>>(b); break;
-                case 4: match_tree_kernel<5><<<blocks, 256, 8 * sizeof(MtWarpMem<5>), st>>>(b); break;
-                default: match_tree_kernel<6><<<blocks, 256, 8 * sizeof(MtWarpMem<6>), st>>>(b); break;
+                case 0: lrc = launch_tree_class<1>(b, dem, st, launches); break;
+                case 1: lrc = launch_tree_class<2>(b, dem, st, launches); break;
+                case 2: lrc = launch_tree_class<3>(b, dem, st, launches); break;
+                case 3: lrc = launch_tree_class<4>(b, dem, st, launches); break;
+                case 4: lrc = launch_tree_class<5>(b, dem, st, launches); break;
+                default: lrc = launch_tree_class<6>(b, dem, st, launches); break;
                 }
-                GQ_CUDA(cudaGetLastError());
-                ++*launches;
+                if (lrc) GQ_FAIL(lrc, "matching decoder: first-tier kernel launch failed");
                 if (c == dom) GQ_CUDA(cudaEventRecord(dec->kev1, st));
                 if (st != dem->stream) {
                     GQ_CUDA(cudaEventRecord(dec->side_done[nside - 1], st));

@@ -24,3 +24,4 @@ static inline unsigned __reduce_xor_sync(unsigned, unsigned v) { return v; }
 static inline void __syncwarp() {}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+struct uint4 { unsigned x, y, z, w; };

@@ -160,7 +160,7 @@ def tree_hostsim():
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
     lib = ctypes.CDLL(so)
     lib.hostsim_mt_decode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
-                                      ctypes.c_long] + [ctypes.c_void_p] * 4
+                                      ctypes.c_long] + [ctypes.c_void_p] * 5
     lib.hostsim_mt_stats.argtypes = [ctypes.c_void_p, ctypes.c_int]
     return lib
 
@@ -179,9 +179,20 @@ def _device_tables(orc):
     return dist, pobs
 
 
-def _tree_decode(lib, orc, dets_b8):
+def _neighbor_lists(dist, D, DW, L=16):
+    """nearest-detector lists as matching.cu builds them: distance << 16 | detector, ascending, padded"""
+    nbr = np.full((D + 2, L), (0xFFFF << 16) | (32 * DW), np.uint32)
+    for s in range(D):
+        d = dist[s, :D].astype(np.uint32)
+        ent = np.sort(((d << 16) | np.arange(D, dtype=np.uint32))[d != 0xFFFF])[:L]
+        nbr[s, :len(ent)] = ent
+    return nbr
+
+
+def _tree_decode(lib, orc, dets_b8, lists=True):
     D = orc.nd
     dist, pobs = _device_tables(orc)
+    nbr = _neighbor_lists(dist, D, (D + 31) // 32) if lists else None
     n = dets_b8.shape[0]
     DW = (D + 31) // 32
     rows = np.zeros((n, DW * 4), np.uint8)
@@ -189,7 +200,8 @@ def _tree_decode(lib, orc, dets_b8):
     rows32 = np.ascontiguousarray(rows).view(np.uint32)
     pred = np.zeros(n, np.uint32); wt = np.zeros(n, np.int32); rc = np.zeros(n, np.int32)
     lib.hostsim_mt_decode(D, dist.ctypes.data, pobs.ctypes.data, DW, rows32.ctypes.data, n,
-                          pred.ctypes.data, wt.ctypes.data, rc.ctypes.data, None)
+                          pred.ctypes.data, wt.ctypes.data, rc.ctypes.data, None,
+                          nbr.ctypes.data if lists else None)
     return pred, wt, rc
 
 
@@ -199,11 +211,12 @@ def test_tree_tier_is_exact_on_surface_code_shots(tree_hostsim):
     dem = code.memory_circuit.detector_error_model(decompose_errors=True)
     orc = po.MwpmOracle(dem)
     dets, _ = po.sample(dem, 3, 3000)
-    pred, wt, rc = _tree_decode(tree_hostsim, orc, dets)
     opred, owt = orc.decode_batch(dets, return_weights=True)
-    assert (rc == 0).all()
-    assert (wt == owt).all()          # every matching is a minimum-weight one
-    assert (pred != opred).mean() < 0.01   # equal-weight optima may differ in the predicted observable
+    for lists in (True, False):   # nearest-detector lists / every defect through the row fallback
+        pred, wt, rc = _tree_decode(tree_hostsim, orc, dets, lists=lists)
+        assert (rc == 0).all()
+        assert (wt == owt).all()          # every matching is a minimum-weight one
+        assert (pred != opred).mean() < 0.01   # equal-weight optima may differ in the predicted observable
 
 
 def test_tree_tier_is_exact_on_random_graphs_with_blossoms(tree_hostsim):
@@ -225,7 +238,7 @@ def test_tree_tier_is_exact_on_random_graphs_with_blossoms(tree_hostsim):
         orc = po.MwpmOracle(edges=edges, num_detectors=D, num_observables=1, int_weights=w)
         bits = (rng.random((200, D)) < rng.choice([0.15, 0.4, 0.8])).astype(np.uint8)
         dets = np.packbits(bits, axis=1, bitorder="little")
-        pred, wt, rc = _tree_decode(tree_hostsim, orc, dets)
+        pred, wt, rc = _tree_decode(tree_hostsim, orc, dets, lists=bool(trial % 2))
         opred, owt = orc.decode_batch(dets, return_weights=True)
         assert (rc == 0).all() and (wt == owt).all(), (trial, np.where(wt != owt)[0][:5])
     tree_hostsim.hostsim_mt_stats(stats, 0)
