@@ -269,7 +269,7 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel: the first-tier matching kernel most shots go through (K3a, match_tree_kernel<K>),
+        # dominant kernel: the blossom-phase kernel of the class most shots fall in (K3a, tree_solve_kernel<K>),
         # timed inside gq_collect with CUDA events on the decoder's stream.  Algorithmic bytes = the
         # bit-packed syndrome + observable of the shots THAT kernel decoded.
         per_launch_ms = k_ms / max(1, k_launches)
@@ -277,7 +277,7 @@ def main():
         achieved = ALG_BYTES_PER_SHOT * shots_per_launch / max(per_launch_ms * 1e-3, 1e-12) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_SHOT * shots_per_launch if NCU_DRAM_BYTES_PER_SHOT else None,
-                "kernel": "match_tree_kernel<%d> (K3a, first tier, shots with %d..%d defects)" % (k_K, 32 * (k_K - 1) + 1, 32 * k_K),
+                "kernel": "tree_solve_kernel<%d> (K3a, blossom phases of the shots with %d..%d defects)" % (k_K, 32 * (k_K - 1) + 1, 32 * k_K),
                 "peak_source": "MEASURED_PEAKS.json (hbm_gbs, burst)" if peaks else "fallback",
                 "kernel_ms_per_launch": per_launch_ms, "shots_per_launch": shots_per_launch,
                 "kernel_share_of_step": k_ms / max(dev_ms, 1e-9),

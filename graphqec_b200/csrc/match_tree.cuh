@@ -176,8 +176,6 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
         kb[k_] = (unsigned)(lane + GQW_LANES * (k_)) | KB_OUTER;                                \
         bk[k_] = b4[k_] < SL_INF ? (((unsigned)(b4[k_] - yb[k_]) << 10) | 0x300u | (unsigned)(lane + GQW_LANES * (k_))) : 0xffffffffu; \
     }
-// uniform scan masks: one vertex / the vertices flagged by a per-lane predicate
-#define GQT_MASK_ONE(u_) { _Pragma("unroll") for (int k_ = 0; k_ < K; ++k_) nm[k_] = (((u_) >> GQW_LOG) == k_) ? (1u << ((u_) & (GQW_LANES - 1))) : 0u; }
 // scan the row of outer vertex u_ (its dual is yb + D): offer its edges to every vertex of other nodes
 #define GQT_SCAN(u_)                                                                            \
     {                                                                                           \
@@ -221,33 +219,32 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
             if (f.mate[root] != -1) continue;   // became the far end of an earlier augmenting path
             // ---- phase: one alternating tree rooted at root
             D = 0;
-            unsigned nm[K];          // warp-uniform masks of the vertices to scan next, per slot
+            unsigned nm[K];          // warp-uniform masks of the vertices to scan next, per slot ...
+            int sv;                  // ... or the single vertex to scan (the common case), -1: use the masks
             bool inner_blossoms = false;   // an inner (T) top-level blossom exists in this tree
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 ek[k] = EK_NONE; slfrom[k] = -1;
                 if (lane + GQW_LANES * k == root) { GQT_MAKE_OUTER(k); f.label[root] = L_S; }
             }
-            GQT_MASK_ONE(root);
+#pragma unroll
+            for (int k = 0; k < K; ++k) nm[k] = 0u;
+            sv = root;
             __syncwarp();
             int vfree = -1;
             for (int guard = 0;; ++guard) {
                 // ---- scan the rows of the vertices that just turned outer (one body, runtime loops)
-                unsigned nm_any = 0;
+                for (;;) {
+                    if (sv < 0) {
+                        // pop the lowest flagged vertex off the masks (blossom events only)
 #pragma unroll
-                for (int k = 0; k < K; ++k) nm_any |= nm[k];
-                if (nm_any) {
-#pragma unroll 1
-                    for (int kk = 0; kk < K; ++kk) {
-                        unsigned m = (unsigned)sel_slot<K>(nm, kk);
-#pragma unroll 1
-                        while (m) {
-                            const int b_ = __ffs(m) - 1;
-                            m &= m - 1;
-                            GQM_STAT(6, 1);
-                            GQT_SCAN(GQW_LANES * kk + b_);
-                        }
+                        for (int k = 0; k < K; ++k)
+                            if (sv < 0 && nm[k]) { sv = GQW_LANES * k + __ffs(nm[k]) - 1; nm[k] &= nm[k] - 1; }
+                        if (sv < 0) break;
                     }
+                    GQM_STAT(6, 1);
+                    GQT_SCAN(sv);
+                    sv = -1;
                 }
                 if (guard > 8 * (cap + FT::nb) + 64) return 3;
                 // ---- earliest event
@@ -268,8 +265,6 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                 const int arg = best & 0xff;
                 int src = -1;
                 if (type < 2) GQT_SEL(slfrom, arg, src);
-#pragma unroll
-                for (int k = 0; k < K; ++k) nm[k] = 0u;
                 if (type == 1 && f.top[src] == f.top[arg]) {
                     GQM_STAT(1, 1);
                     // stale: the source was swallowed by the target's blossom -> recompute the best
@@ -332,7 +327,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                             GQT_MAKE_OUTER(k);
                         }
                     }
-                    if (sn < cap) { GQT_MASK_ONE(sn); }
+                    if (sn < cap) sv = sn;
                     else {
 #pragma unroll
                         for (int k = 0; k < K; ++k) nm[k] = __ballot_sync(GQW_FULL, turned[k]);
@@ -460,7 +455,6 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
 #undef GQT_IS_OUTER
 #undef GQT_IS_INNER
 #undef GQT_MAKE_OUTER
-#undef GQT_MASK_ONE
 #undef GQT_SCAN
 }
 
