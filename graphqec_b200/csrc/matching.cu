@@ -439,7 +439,10 @@ __global__ void __launch_bounds__(256) tree_start_kernel(MatchArgs a) {
     }
 }
 
-template <int K>
+// EXTRAS = weights / flags / corrections requested (tests, sinter's syndrome-reproduction checks): the
+// throughput instantiation leaves that code out, which is worth it because the kernel is at the edge of
+// the instruction cache
+template <int K, bool EXTRAS>
 __global__ void __launch_bounds__(256, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : 2))) tree_solve_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(256, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_
     const StartRecord<K> *recs = reinterpret_cast<const StartRecord<K> *>(a.ws);
     gqt::Tables T;
     T.dist = a.dist; T.pobs = a.pobs; T.D = a.D; T.N = a.N; T.nbr = a.nbr;
-    const bool want_weight = a.weight_out != nullptr;
+    const bool want_weight = EXTRAS && a.weight_out != nullptr;
 
     for (uint32_t item = warp; item < a.nitems; item += nwarps) {
         const uint32_t shot = a.list[item];
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(256, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_
             __syncwarp();
             continue;
         }
-        if (rc == 0 && a.corr_out) {
+        if (EXTRAS && rc == 0 && a.corr_out) {
             uint32_t *corr_row = a.corr_out + (size_t)shot * a.EW;
 #pragma unroll 1
             for (int i = lane; i < n0; i += 32) {
@@ -491,8 +494,8 @@ __global__ void __launch_bounds__(256, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_
             a.pred[(size_t)shot * a.OW] = rc == 0 ? pm : 0u;
 #pragma unroll 1
             for (uint32_t w = 1; w < a.OW; ++w) a.pred[(size_t)shot * a.OW + w] = 0u;
-            if (a.weight_out) a.weight_out[shot] = rc == 0 ? wt : -1;
-            if (a.flags_out) a.flags_out[shot] = (uint8_t)(rc == 0 ? 0 : 1);
+            if (EXTRAS && a.weight_out) a.weight_out[shot] = rc == 0 ? wt : -1;
+            if (EXTRAS && a.flags_out) a.flags_out[shot] = (uint8_t)(rc == 0 ? 0 : 1);
         }
         __syncwarp();
     }
@@ -506,7 +509,8 @@ static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, i
     const int per_sm = K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : 2);
     const int blocks_b = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * per_sm);
     if (ev0) cudaEventRecord(ev0, st);   // bench.py's roofline times the solve kernel of the biggest class
-    tree_solve_kernel<K><<<blocks_b, 256, 8 * sizeof(MtWarpMem<K>), st>>>(b);
+    if (b.weight_out || b.flags_out || b.corr_out) tree_solve_kernel<K, true><<<blocks_b, 256, 8 * sizeof(MtWarpMem<K>), st>>>(b);
+    else tree_solve_kernel<K, false><<<blocks_b, 256, 8 * sizeof(MtWarpMem<K>), st>>>(b);
     if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
     if (ev1) cudaEventRecord(ev1, st);
     *launches += 2;
@@ -516,7 +520,8 @@ static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, i
 template <int K>
 static int configure_tree_class() {
     if (cudaFuncSetAttribute(tree_start_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(StartWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
-    if (cudaFuncSetAttribute(tree_solve_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
+    if (cudaFuncSetAttribute(tree_solve_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
+    if (cudaFuncSetAttribute(tree_solve_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
     return GQ_OK;
 }
 
