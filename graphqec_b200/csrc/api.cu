@@ -31,6 +31,10 @@ __global__ void sm_to_b8_kernel(const uint32_t *src, uint32_t OW, uint32_t row_b
     }
 }
 
+#ifndef GQ_COLLECT_CHUNK_LOG2
+#define GQ_COLLECT_CHUNK_LOG2 22   // = matching.cu's decode slice: per-slice launch overheads and tails amortise over 4M shots
+#endif
+
 static void default_params(gq_decoder_params *p) {
     memset(p, 0, sizeof(*p));
     p->weight_levels = 1000;
@@ -226,7 +230,7 @@ extern "C" int gq_collect(gq_dem *dem, gq_dec *dec, uint64_t seed, uint64_t shot
     out[0] = out[1] = out[2] = 0;
     if (nshots == 0) return GQ_OK;
     GQ_CUDA(cudaSetDevice(dem->device));
-    const uint64_t chunk = 1ull << 20;  // multiple of every tile size
+    const uint64_t chunk = 1ull << GQ_COLLECT_CHUNK_LOG2;  // multiple of every tile size
     int rc = ensure_scratch(dec, std::min(chunk, nshots));
     if (rc) return rc;
     cudaEvent_t ev[4];

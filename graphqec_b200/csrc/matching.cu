@@ -318,6 +318,9 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
 #ifndef GQ_MT_PER_SM
 #define GQ_MT_PER_SM 4
 #endif
+#ifndef GQ_SLICE_LOG2
+#define GQ_SLICE_LOG2 22   // shots per decode slice (lists, hand-off records and launch overheads are per slice)
+#endif
 #ifndef GQ_MT_PER_SM_K4
 #define GQ_MT_PER_SM_K4 4
 #endif
@@ -743,14 +746,14 @@ int gq_matching_create(gq_dec *dec) {
     if (configure_tree_class<1>() || configure_tree_class<2>() || configure_tree_class<3>() || configure_tree_class<4>() ||
         configure_tree_class<5>() || configure_tree_class<6>())
         GQ_FAIL(GQ_E_CUDA, "matching decoder: cudaFuncSetAttribute failed for the first-tier kernels");
-    GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << 20) + 16) * 4));
+    GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << GQ_SLICE_LOG2) + 16) * 4));
     for (int i = 0; i < 5; ++i) {
         GQ_CUDA(cudaStreamCreateWithFlags(&dec->side_streams[i], cudaStreamNonBlocking));
         GQ_CUDA(cudaEventCreateWithFlags(&dec->side_done[i], cudaEventDisableTiming));
     }
     GQ_CUDA(cudaEventCreate(&dec->kev0));
     GQ_CUDA(cudaEventCreate(&dec->kev1));
-    dec->overflow_cap = 1u << 20;
+    dec->overflow_cap = 1u << GQ_SLICE_LOG2;   // a whole slice may overflow (dense syndromes)
     GQ_CUDA(cudaMalloc((void **)&dec->d_overflow, 2 * (2 + (size_t)dec->overflow_cap) * 4));
     return GQ_OK;
 }
@@ -787,7 +790,7 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
     a.dist = dec->d_dist; a.pobs = dec->d_pobs; a.next = dec->d_next; a.nbr = dec->d_nbr;
     a.adj_ptr = dec->d_adj_ptr; a.adj_node = dec->d_adj_node; a.adj_edge = dec->d_adj_edge;
     // the overflow lists are bounded: process in slices so they can never overrun
-    const uint64_t slice = 1ull << 20;
+    const uint64_t slice = 1ull << GQ_SLICE_LOG2;
     uint32_t *ovf_buf[2] = {dec->d_overflow, dec->d_overflow + 2 + dec->overflow_cap};
     for (uint64_t s0 = 0; s0 < nshots; s0 += slice) {
         uint64_t ns = std::min(slice, nshots - s0);

@@ -6,7 +6,7 @@ be.library_path = lambda: libpath
 import bench
 dem = bench.north_star_dem()
 h = be.DemHandle(dem); d = be.DecoderHandle(h, be.MATCHING)
-n = 1 << 20
+n = int(os.environ.get("LB_SHOTS", 1 << 20))
 d.collect(1, 0, n, 0)
 ts = []
 for k in range(3):
