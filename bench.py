@@ -34,10 +34,11 @@ SEED = 20261019
 WORKLOAD = "RotatedSurfaceCode d=11 r=11 p=0.005 Z-memory (BASELINE configs[1], north-star point)"
 ALG_BYTES_PER_SHOT = (1320 + 1) / 8.0   # bit-packed syndrome + observable per shot
 # from the committed ncu --set full capture of the dominant kernel (profiles/, this round); None = not captured
-# profiles/r01_match_tree_kernel3_v4_summary.txt: 163.4 MB read + 6.6 MB written / 767150 shots, 6.998e9 warp-instructions
-NCU_DRAM_BYTES_PER_SHOT = (163.376384e6 + 6.583808e6) / 767150
-NCU_WARP_INSTR_PER_SHOT = 6998043045 / 767150
-NCU_ISSUE_ACTIVE_PCT = 63.9
+# profiles/r01_tree_solve_kernel3_v5_summary.txt: 1.866 GB read + 22.8 MB written / 3 068 601 shots (the hand-off
+# records are 592 B/shot of that), 1.991e10 warp-instructions, 72.3 % of issue slots active
+NCU_DRAM_BYTES_PER_SHOT = (1.865764e9 + 22.793984e6) / 3068601
+NCU_WARP_INSTR_PER_SHOT = 19910301124 / 3068601
+NCU_ISSUE_ACTIVE_PCT = 72.3
 
 
 def north_star_dem():

@@ -409,7 +409,7 @@ struct StartWarpMem {
 };
 
 template <int K>
-__global__ void __launch_bounds__(256) tree_start_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(256, 8) tree_start_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(256, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_
 
 template <int K>
 static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, int *launches, cudaEvent_t ev0, cudaEvent_t ev1) {
-    const int blocks_a = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * 6);
+    const int blocks_a = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * 8);   // latency-bound: all 64 warps/SM
     tree_start_kernel<K><<<blocks_a, 256, 8 * sizeof(StartWarpMem<K>), st>>>(b);
     if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
     const int per_sm = K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : 2);

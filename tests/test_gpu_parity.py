@@ -257,6 +257,39 @@ def test_decode_b8_host_path_equals_device_path():
         dech.decode_b8(np.zeros((4, 3), dtype=np.uint8))
 
 
+def test_decode_b8_pipelined_chunks_equal_device_path():
+    """a host batch long enough to be cut into several chunks (H2D of chunk c+1 overlaps the decode of c)
+    decodes exactly like the device-resident path, ragged tail included"""
+    dem, demh, dech = case("rep7")
+    n = (1 << 19) + 64 * demh.tile_shots + 0   # > 2^19 shots: gq_decode_b8 cuts it into 2^18-shot chunks
+    dets, obs = demh.sample(33, 0, n)
+    n_ragged = n - 77
+    pred = dech.decode(dets[:n_ragged])
+    out = dech.decode_b8(b8(dets[:n_ragged], dem.num_detectors))
+    assert out.shape == (n_ragged, 1)
+    assert (out == b8(pred, dem.num_observables)).all()
+
+
+def test_every_first_tier_class_and_the_ladder_give_the_optimum():
+    """syndromes with 1 .. 300 defects: classes K = 1..6 of the first tier, then the older tiers"""
+    import torch
+    dem, demh, dech = case("rot7")
+    rng = np.random.default_rng(3)
+    D = dem.num_detectors
+    counts = [1, 2, 31, 32, 33, 64, 65, 96, 97, 128, 129, 160, 161, 192, 193, 255, 256, 300]
+    rows = np.zeros((len(counts) * 3, demh.DW), dtype=np.uint32)
+    for i, c in enumerate(counts * 3):
+        for k in rng.choice(D, size=min(c, D), replace=False):
+            rows[i, k >> 5] |= np.uint32(1) << np.uint32(k & 31)
+    t = torch.from_numpy(rows.view(np.int32)).cuda()
+    pred, wts, flags = dech.decode(t, want_weights=True, want_flags=True)
+    orc, _ = oracle_for(dem, dech)
+    opred, owts = orc.decode_batch(b8(t, D), return_weights=True)
+    assert (flags == 0).all() and (wts.cpu().numpy() == owts).all()
+    # the throughput instantiation (no weights / flags requested) must predict the same
+    assert (dech.decode(t) == pred).all()
+
+
 def test_count_and_collect_agree():
     dem, demh, dech = case("rot5")
     n = 40 * demh.tile_shots
