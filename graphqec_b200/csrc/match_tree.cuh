@@ -221,6 +221,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
             D = 0;
             unsigned nm[K];          // warp-uniform masks of the vertices to scan next, per slot ...
             int sv;                  // ... or the single vertex to scan (the common case), -1: use the masks
+            bool have_masks = false; // nm[] may hold vertices (set by the blossom events only)
             bool inner_blossoms = false;   // an inner (T) top-level blossom exists in this tree
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -232,21 +233,23 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
             sv = root;
             __syncwarp();
             int vfree = -1;
-            for (int guard = 0;; ++guard) {
+            int fail = 0;
+            for (int guard = 8 * (cap + FT::nb) + 64;; --guard) {
                 // ---- scan the rows of the vertices that just turned outer (one body, runtime loops)
                 for (;;) {
                     if (sv < 0) {
+                        if (!have_masks) break;
                         // pop the lowest flagged vertex off the masks (blossom events only)
 #pragma unroll
                         for (int k = 0; k < K; ++k)
                             if (sv < 0 && nm[k]) { sv = GQW_LANES * k + __ffs(nm[k]) - 1; nm[k] &= nm[k] - 1; }
-                        if (sv < 0) break;
+                        if (sv < 0) { have_masks = false; break; }
                     }
                     GQM_STAT(6, 1);
                     GQT_SCAN(sv);
                     sv = -1;
                 }
-                if (guard > 8 * (cap + FT::nb) + 64) return 3;
+                if (guard < 0) { fail = 3; break; }
                 // ---- earliest event
                 unsigned best = 0xffffffffu;
 #pragma unroll
@@ -259,7 +262,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                 }
                 best = __reduce_min_sync(GQW_FULL, best);
                 GQM_STAT(0, 1);
-                if (best >= 0x7ffffc00u) return 1;
+                if (best >= 0x7ffffc00u) { fail = 1; break; }
                 const i32 t = (i32)(best >> 10);
                 const int type = (best >> 8) & 3;
                 const int arg = best & 0xff;
@@ -331,6 +334,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     else {
 #pragma unroll
                         for (int k = 0; k < K; ++k) nm[k] = __ballot_sync(GQW_FULL, turned[k]);
+                        have_masks = true;
                     }
                     __syncwarp();
                 } else if (type == 3) {
@@ -360,7 +364,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                         }
                     }
                     b = __shfl_sync(GQW_FULL, b, 0);
-                    if (b < 0) return 2;
+                    if (b < 0) { fail = 2; break; }
                     bhi = max(bhi, b - cap + 1);
                     __syncwarp();
 #pragma unroll
@@ -379,6 +383,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                         }
                         nm[k] = __ballot_sync(GQW_FULL, turned);
                     }
+                    have_masks = true;
                     __syncwarp();
                 } else {
                     GQM_STAT(7, 1);
@@ -425,8 +430,10 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                         }
                         nm[k] = __ballot_sync(GQW_FULL, turned);
                     }
+                    have_masks = true;
                 }
             }
+            if (fail) return fail;
             // ---- phase end: the tree dissolves, duals leave the clock
             __syncwarp();
             if (bhi) {
