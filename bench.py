@@ -54,23 +54,48 @@ def north_star_dem():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML (pynvml, ~1 ms per sample, every
+    10 ms) when importable, else the nvidia-smi query of the profiling recipe (one sample per ~0.2 s)."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") else n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        flags = []
+        for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)):
+            flags.append("Active" if r & bit else "Not Active")
+        return [str(sm), str(mx), ""] + flags
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self._nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -90,7 +115,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def cpu_baseline(dem, seconds_target: float = 15.0, threads: int | None = None):
@@ -207,10 +232,6 @@ def main():
         got = dech.collect(SEED, (k * world + rank) * shots, shots, 0)
         t = dech.last_timing()
         t["kernel"] = dech.last_kernel_profile()
-        if world > 1:
-            counts.copy_(torch.tensor(got, dtype=torch.int64))
-            dist.all_reduce(counts)       # the path's only exchange: (shots, errors, discards)
-            got = tuple(int(x) for x in counts.tolist())
         return got, t
 
     for w in range(max(args.warmup, 3) if args.warmup else 0):
@@ -230,6 +251,11 @@ def main():
             launches += t["launches"]
             kp = t["kernel"]
             k_ms += kp["ms"]; k_launches += kp["launches"]; k_shots += kp["shots"]; k_K = kp["K"]
+        if world > 1:
+            # the path's only exchange: one all-reduce of (shots, errors, discards) over NVLink, inside the timed region
+            counts.copy_(torch.tensor([tot_shots, tot_err, 0], dtype=torch.int64))
+            dist.all_reduce(counts)
+            tot_shots, tot_err = (int(x) for x in counts.tolist()[:2])
         barrier()
         dt = time.perf_counter() - t0
     tmax = torch.tensor([dt], dtype=torch.float64, device=dev)

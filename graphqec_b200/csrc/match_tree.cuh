@@ -492,9 +492,13 @@ __device__ __forceinline__ void dual_start(const Tables &T, i16 *xch, const u16 
         if (synw != nullptr) {
             const uint4 *L = reinterpret_cast<const uint4 *>(T.nbr + (size_t)dj[k] * NBR_LEN);
             uint32_t hit = 0xffffffffu;
-#pragma unroll 1   // rolled on purpose: the kernels are instruction-fetch sensitive
+            uint4 le[NBR_LEN / 4];   // all list loads in flight before the first test (the start kernel is small
+                                     // enough for the unrolled body; it is latency-bound)
+#pragma unroll
+            for (int c = 0; c < NBR_LEN / 4; ++c) le[c] = L[c];
+#pragma unroll
             for (int c = NBR_LEN / 4 - 1; c >= 0; --c) {
-                const uint4 e = L[c];
+                const uint4 e = le[c];
                 const uint32_t ent[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
                 for (int q = 3; q >= 0; --q) {
