@@ -223,18 +223,25 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
             int sv;                  // ... or the single vertex to scan (the common case), -1: use the masks
             bool have_masks = false; // nm[] may hold vertices (set by the blossom events only)
             bool inner_blossoms = false;   // an inner (T) top-level blossom exists in this tree
+            {
+                // the root turns outer: its key bits and boundary event are formed once (warp-uniform slot)
+                const bool mine = lane == (root & (GQW_LANES - 1));
+                const i32 rb4 = (i32)sel_slot<K>(b4, rk), ryb = (i32)sel_slot<K>(yb, rk);
+                const unsigned rbk = rb4 < SL_INF ? (((unsigned)(rb4 - ryb) << 10) | 0x300u | (unsigned)root) : 0xffffffffu;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                ek[k] = EK_NONE; slfrom[k] = -1;
-                if (lane + GQW_LANES * k == root) { GQT_MAKE_OUTER(k); f.label[root] = L_S; }
+                for (int k = 0; k < K; ++k) {
+                    ek[k] = EK_NONE; slfrom[k] = -1;
+                    if (mine && k == rk) { kb[k] = (unsigned)root | KB_OUTER; bk[k] = rbk; }
+                }
+                if (mine) f.label[root] = L_S;
             }
 #pragma unroll
             for (int k = 0; k < K; ++k) nm[k] = 0u;
             sv = root;
             __syncwarp();
-            int vfree = -1;
             int fail = 0;
-            for (int guard = 8 * (cap + FT::nb) + 64;; --guard) {
+            int guard = 8 * (cap + FT::nb) + 64;   // bounds the blossom events of a phase (grow steps are bounded by n)
+            for (;;) {
                 // ---- scan the rows of the vertices that just turned outer (one body, runtime loops)
                 for (;;) {
                     if (sv < 0) {
@@ -249,7 +256,6 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     GQT_SCAN(sv);
                     sv = -1;
                 }
-                if (guard < 0) { fail = 3; break; }
                 // ---- earliest event
                 unsigned best = 0xffffffffu;
 #pragma unroll
@@ -268,32 +274,11 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                 const int arg = best & 0xff;
                 int src = -1;
                 if (type < 2) GQT_SEL(slfrom, arg, src);
-                if (type == 1 && f.top[src] == f.top[arg]) {
-                    GQM_STAT(1, 1);
-                    // stale: the source was swallowed by the target's blossom -> recompute the best
-                    // edge from the outer vertices of other nodes into arg
-                    const int tv = f.top[arg];
-                    i32 yv;
-                    GQT_SEL(yb, arg, yv);
-                    yv += D;
-                    const uint32_t ro = (uint32_t)def[arg] * N;
-                    unsigned bb = 0xffffffffu;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const i32 wt = (i32)dist[ro + dj[k]];
-                        const i32 s = 4 * wt - yv - (yb[k] + D);
-                        if (GQT_IS_OUTER(k) && vtop[k] != tv && wt != (i32)W_INF)
-                            bb = min(bb, ((unsigned)s << 8) | (unsigned)(lane + GQW_LANES * k));
-                    }
-                    bb = __reduce_min_sync(GQW_FULL, bb);
-#pragma unroll
-                    for (int k = 0; k < K; ++k)
-                        if (lane + GQW_LANES * k == arg) {
-                            ek[k] = bb == 0xffffffffu ? EK_NONE : ((((unsigned)D + (bb >> 9)) << 10) | 0x100u | (unsigned)arg);
-                            slfrom[k] = bb == 0xffffffffu ? -1 : (int)(bb & 0xff);
-                        }
-                    continue;
-                }
+#ifdef GQ_HOST_SIM
+                // stale entries (source and target in one node) are dropped when their blossom forms, so none
+                // can win the search; the host build checks that
+                if (type == 1 && f.top[src] == f.top[arg]) { GQM_STAT(1, 1); fail = 3; break; }
+#endif
                 D = t;
                 if (type == 0) {
                     // ---- an outer vertex reaches an unlabelled node
@@ -305,7 +290,6 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                         // (m == -2): u takes it over; a boundary match is simply released
                         GQM_STAT(4, 1);
                         if (lane == 0) { if (tn >= cap) gqr::rebase(f, tn, v); gqr::augment(f, u, v); }
-                        if (m == -1) vfree = v;
                         break;
                     }
                     GQM_STAT(2, 1);
@@ -344,6 +328,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     break;
                 } else if (type == 1) {
                     GQM_STAT(3, 1);
+                    if (--guard < 0) { fail = 3; break; }
                     // ---- odd cycle: shrink
                     const int v = arg, u = src;
 #pragma unroll 1
@@ -367,13 +352,14 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     if (b < 0) { fail = 2; break; }
                     bhi = max(bhi, b - cap + 1);
                     __syncwarp();
+                    bool turned[K];
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const int x = lane + GQW_LANES * k;
-                        bool turned = false;
+                        turned[k] = false;
                         if (x < n && f.par[vtop[k]] == b) {
                             if (GQT_IS_INNER(k)) {
-                                turned = true;
+                                turned[k] = true;
                                 yb[k] -= 2 * D;
                                 ek[k] = ek_has(ek[k]) ? (((unsigned)(D + (ek_time(ek[k]) >> 1)) << 10) | 0x100u | (unsigned)x) : EK_NONE;
                                 GQT_MAKE_OUTER(k);
@@ -381,12 +367,23 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                             vtop[k] = b;
                             f.top[x] = (i16)b;
                         }
-                        nm[k] = __ballot_sync(GQW_FULL, turned);
+                    }
+                    __syncwarp();
+                    // an entry whose source now sits in the same blossom is void: drop it and offer the vertex's
+                    // row again (every edge to another node is then held by the far end at least), so that no
+                    // stale entry can ever win the search
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        if (vtop[k] == b && slfrom[k] >= 0 && ek_has(ek[k]) && f.top[slfrom[k]] == b) {
+                            ek[k] = EK_NONE; slfrom[k] = -1; turned[k] = true;
+                        }
+                        nm[k] = __ballot_sync(GQW_FULL, turned[k]);
                     }
                     have_masks = true;
                     __syncwarp();
                 } else {
                     GQM_STAT(7, 1);
+                    if (--guard < 0) { fail = 3; break; }
                     // ---- an inner blossom's dual reached zero: expand (its children may be inner blossoms)
                     const int b = cap + arg;
                     inner_blossoms = true;
@@ -452,7 +449,6 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     kb[k] = (unsigned)x; bk[k] = 0xffffffffu;
                     f.label[vtop[k]] = L_NONE;
                 }
-                if (x == root || x == vfree) freebits &= ~GQW_BIT(k);
             }
             __syncwarp();
         }
