@@ -34,11 +34,11 @@ SEED = 20261019
 WORKLOAD = "RotatedSurfaceCode d=11 r=11 p=0.005 Z-memory (BASELINE configs[1], north-star point)"
 ALG_BYTES_PER_SHOT = (1320 + 1) / 8.0   # bit-packed syndrome + observable per shot
 # from the committed ncu --set full capture of the dominant kernel (profiles/, this round); None = not captured
-# profiles/r01_tree_solve_kernel3_v5_summary.txt: 1.866 GB read + 22.8 MB written / 3 068 601 shots (the hand-off
-# records are 592 B/shot of that), 1.991e10 warp-instructions, 72.3 % of issue slots active
-NCU_DRAM_BYTES_PER_SHOT = (1.865764e9 + 22.793984e6) / 3068601
-NCU_WARP_INSTR_PER_SHOT = 19910301124 / 3068601
-NCU_ISSUE_ACTIVE_PCT = 72.3
+# profiles/r01_tree_solve_kernel3_v6_summary.txt: 464.8 MB read + 8.0 MB written / 767 034 shots (the hand-off
+# records are ~6 B per defect + 16 B of that), 4.198e9 warp-instructions, 70.2 % of issue slots active
+NCU_DRAM_BYTES_PER_SHOT = (464.755712e6 + 7.965184e6) / 767034
+NCU_WARP_INSTR_PER_SHOT = 4198034323 / 767034
+NCU_ISSUE_ACTIVE_PCT = 70.2
 
 
 def north_star_dem():

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "gq_common.h"
 
@@ -144,10 +145,26 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
     // Software pipeline over chunks: the H2D copy of chunk c+1 runs on a second stream while chunk c is
     // decoded (the decoder synchronises its own stream with the host; the copy stream keeps going).
     // Two raw-input buffers; a buffer is free again once its rows were re-strided into d_dets.
-    // (chunks of 2^20 shots keep the decoder's per-slice launch overhead small; calls too short for two
-    // of those are cut into 2^18-shot chunks so that their copy still overlaps)
-    const uint64_t chunk = nshots >= (1ull << 21) ? (1ull << 20) : (nshots > (1ull << 19) ? (1ull << 18) : (1ull << 20));
-    const uint64_t nchunks = (nshots + chunk - 1) / chunk;
+    // Chunk schedule: 2^18, 2^19, 2^20, then 2^21 shots -- a short first chunk keeps the one copy that cannot
+    // overlap anything short, each later copy hides behind the decode of the chunk before it (the decoder is
+    // ~4x slower than PCIe), and the big chunks amortise the decoder's per-slice launch overheads and tails.
+    // A remainder shorter than 2^19 shots rides with the chunk before it.
+    std::vector<uint64_t> cstart;
+    uint64_t chunk = 0;
+    {
+        uint64_t at = 0, sz = nshots >= (1ull << 21) ? (1ull << 18) : (nshots > (1ull << 19) ? (1ull << 18) : (1ull << 20));
+        const bool grow = nshots >= (1ull << 21);
+        while (at < nshots) {
+            uint64_t ns = std::min(sz, nshots - at);
+            if (nshots - at - ns < (1ull << 19) && grow) ns = nshots - at;
+            cstart.push_back(at);
+            chunk = std::max(chunk, ns);
+            at += ns;
+            if (grow && sz < (1ull << 21)) sz <<= 1;
+        }
+        cstart.push_back(nshots);
+    }
+    const uint64_t nchunks = cstart.size() - 1;
     if (!dec->copy_stream) {
         GQ_CUDA(cudaStreamCreateWithFlags(&dec->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
@@ -174,7 +191,7 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
     uint8_t *d_in[2] = {dec->d_b8, dec->d_b8 + chunk * db};
     uint8_t *d_out = dec->d_b8 + 2 * chunk * db;
     auto issue_copy = [&](uint64_t c) -> int {
-        const uint64_t s0 = c * chunk, ns = std::min(chunk, nshots - s0);
+        const uint64_t s0 = cstart[c], ns = cstart[c + 1] - s0;
         const int buf = (int)(c & 1);
         if (c >= 2) GQ_CUDA(cudaStreamWaitEvent(dec->copy_stream, dec->ev_consumed[buf], 0));
         GQ_CUDA(cudaMemcpyAsync(d_in[buf], dets_b8 + s0 * db, ns * db, cudaMemcpyHostToDevice, dec->copy_stream));
@@ -185,7 +202,7 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
     rc = issue_copy(0);
     if (rc) return rc;
     for (uint64_t c = 0; c < nchunks; ++c) {
-        const uint64_t s0 = c * chunk, ns = std::min(chunk, nshots - s0);
+        const uint64_t s0 = cstart[c], ns = cstart[c + 1] - s0;
         const int buf = (int)(c & 1);
         if (c + 1 < nchunks) { rc = issue_copy(c + 1); if (rc) return rc; }
         GQ_CUDA(cudaEventRecord(e0, dem->stream));

@@ -13,9 +13,21 @@ for r in rows:
         try: agg[(cur, int(r[0]))] = (int(d.get("Instructions Executed", 0) or 0), int(d.get("# Samples", 0) or 0))
         except ValueError: pass
 tot = sum(v[0] for v in agg.values())
-MT = [(0, "prologue/other"), (198, "init"), (213, "root loop"), (220, "phase start"), (237, "scan queue"), (249, "SCAN"), (250, "scan queue"), (253, "search"), (269, "sel src/stale check"), (272, "stale recompute"),
-      (297, "grow"), (303, "augment(free/bdry target)"), (311, "grow"), (340, "bdry augment"), (345, "shrink handler"), (388, "expand handler"), (436, "phase end"), (460, "after"), (468, "dual_start"), (571, "solve_predict"), (640, "x")]
 import os
+mt_text = open(os.path.join(os.path.dirname(__file__), "..", "graphqec_b200", "csrc", "match_tree.cuh")).read().split("\n")
+def at(marker, start=0):
+    for i in range(start, len(mt_text)):
+        if marker in mt_text[i]: return i + 1
+    raise KeyError(marker)
+s0 = at("__device__ __forceinline__ int solve_tree(")
+MT = [(0, "prologue/other"), (at("for (int x = lane; x < n; x += GQW_LANES) {", s0) - 1, "init"), (at("for (int rk = 0; rk < K; ++rk) {", s0) - 1, "root loop"),
+      (at("// ---- phase: one alternating tree", s0), "phase start"), (at("// ---- scan the rows of the vertices", s0), "scan queue"),
+      (at("GQT_SCAN(sv);", s0), "SCAN"), (at("GQT_SCAN(sv);", s0) + 1, "scan queue"), (at("// ---- earliest event", s0), "search"),
+      (at("int src = -1;", s0), "sel src"), (at("if (type == 0) {", s0), "grow"), (at("if (m < 0) {", s0), "augment(free/bdry target)"),
+      (at("GQM_STAT(2, 1);", s0), "grow"), (at("} else if (type == 3) {", s0), "bdry augment"), (at("} else if (type == 1) {", s0), "shrink handler"),
+      (at("// an entry whose source now sits", s0), "shrink: drop void entries"),
+      (at("GQM_STAT(7, 1);", s0) - 1, "expand handler"), (at("// ---- phase end", s0) - 1, "phase end"), (at("return 0;", s0), "after"),
+      (at("void dual_start("), "dual_start"), (at("int solve_predict("), "solve_predict"), (at("int decode_shot("), "x")]
 text = open(os.path.join(os.path.dirname(__file__), "..", "graphqec_b200", "csrc", "blossom_regs.cuh")).read().split("\n")
 fn_starts = [(i + 1, m.group(1)) for i, l in enumerate(text) for m in [re.match(r"^(?:template.*>\s*)?__device__.*?\b(\w+)\(", l)] if m]
 reg = collections.Counter(); samp = collections.Counter()

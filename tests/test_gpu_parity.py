@@ -270,6 +270,18 @@ def test_decode_b8_pipelined_chunks_equal_device_path():
     assert (out == b8(pred, dem.num_observables)).all()
 
 
+def test_decode_b8_growing_chunk_schedule_equals_device_path():
+    """>= 2^21 shots: chunks of 2^18, 2^19, 2^20, 2^21 ... shots, a short remainder riding with the last one"""
+    dem, demh, dech = case("rep7")
+    n = (1 << 22) + (1 << 18) + 5 * demh.tile_shots
+    dets, obs = demh.sample(34, 0, n)
+    n_ragged = n - 13
+    pred = dech.decode(dets[:n_ragged])
+    out = dech.decode_b8(b8(dets[:n_ragged], dem.num_detectors))
+    assert out.shape == (n_ragged, 1)
+    assert (out == b8(pred, dem.num_observables)).all()
+
+
 def test_every_first_tier_class_and_the_ladder_give_the_optimum():
     """syndromes with 1 .. 300 defects: classes K = 1..6 of the first tier, then the older tiers"""
     import torch
