@@ -219,6 +219,9 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
             if (f.mate[root] != -1) continue;   // became the far end of an earlier augmenting path
             // ---- phase: one alternating tree rooted at root
             D = 0;
+#ifdef GQ_MT_STATS
+            int ph_events = 0;
+#endif
             unsigned nm[K];          // warp-uniform masks of the vertices to scan next, per slot ...
             int sv;                  // ... or the single vertex to scan (the common case), -1: use the masks
             bool have_masks = false; // nm[] may hold vertices (set by the blossom events only)
@@ -268,6 +271,9 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                 }
                 best = __reduce_min_sync(GQW_FULL, best);
                 GQM_STAT(0, 1);
+#ifdef GQ_MT_STATS
+                ++ph_events;
+#endif
                 if (best >= 0x7ffffc00u) { fail = 1; break; }
                 const i32 t = (i32)(best >> 10);
                 const int type = (best >> 8) & 3;
@@ -288,7 +294,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     if (m < 0) {
                         // the node is free (m == -1, a plain vertex) or sits on the boundary
                         // (m == -2): u takes it over; a boundary match is simply released
-                        GQM_STAT(4, 1);
+                        GQM_STAT(4, 1); GQM_STAT(10 + (ph_events > 4 ? 4 : ph_events), 1); if (m == -1) GQM_STAT(15, 1);
                         if (lane == 0) { if (tn >= cap) gqr::rebase(f, tn, v); gqr::augment(f, u, v); }
                         break;
                     }
@@ -323,7 +329,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     __syncwarp();
                 } else if (type == 3) {
                     // ---- an outer vertex reaches the boundary: the tree augments onto it
-                    GQM_STAT(4, 1);
+                    GQM_STAT(4, 1); GQM_STAT(10 + (ph_events > 4 ? 4 : ph_events), 1);
                     if (lane == 0) gqr::augment_half(f, arg, -2);
                     break;
                 } else if (type == 1) {

@@ -130,13 +130,19 @@ class ThresholdLAB:
     # ------------------------------------------------------------------ the hot path (A3)
     def collect_stats(self, num_workers: int | None = None, max_shots: int = 10**4,
                       max_errors: int = 1000, decoder_params: dict | None = None,
-                      logic_check: str = "Z") -> None:
+                      logic_check: str = "Z", *, save_resume_filepath: str | None = None) -> None:
         """Run every task until ``max_shots`` shots or ``max_errors`` failures; fills ``samples``.
 
         ``num_workers`` is accepted for signature compatibility (sinter's CPU worker count,
         threshold_lab.py:170-171); the GPU path uses one process per GPU instead.
         ``decoder_params`` may carry backend options: ``seed``, ``device``, ``batch_shots``,
         ``weight_levels``, ``bp_max_iter``, ``bp_alpha``.
+
+        ``save_resume_filepath`` (keyword only; the argument of ``sinter.collect`` the reference never
+        wired up, threshold_lab.py:182-189): a CSV in sinter's schema.  Rows already in it count towards
+        ``max_shots`` / ``max_errors`` of the task with the same ``strong_id``; what this call adds is
+        appended as one row per task (rank 0 writes).  New shots continue the task's counter-based RNG stream
+        behind the recorded ones (from the next whole tile), so a resumed sweep never re-uses a shot.
         """
         from graphqec_b200 import backend as be
 
@@ -155,14 +161,33 @@ class ThresholdLAB:
         max_shots = int(max_shots)
         max_errors = int(max_errors)
 
+        save_resume_filepath = save_resume_filepath or opts.get("save_resume_filepath")
+        prior = {}
+        if save_resume_filepath:
+            from graphqec_b200.stats import append_stats_to_csv, read_stats_from_csv
+
+            prior = {st.strong_id: st for st in read_stats_from_csv(save_resume_filepath)}
+
         samples = []
         for task_index, task in enumerate(self.generate_sinter_tasks(logic_check=logic_check)):
             t0 = time.perf_counter()
             dem = _auto_dem(task.circuit)
             shots = errors = discards = 0
-            if dem.num_errors == 0 or max_shots <= 0:
+            strong_id = task.strong_id(self.decoder)
+            before = prior.get(strong_id)
+            todo_shots, todo_errors, shot0 = max_shots, max_errors, 0
+            if before is not None:
+                todo_shots = max(0, max_shots - before.shots)
+                if max_errors > 0:
+                    todo_errors = max_errors - before.errors
+                    if todo_errors <= 0:
+                        todo_shots = 0
+                shot0 = before.shots
+            if todo_shots <= 0:
+                pass
+            elif dem.num_errors == 0:
                 # p = 0: nothing can fire, nothing to decode (SURVEY 8a, A6 note on p = 0)
-                shots = max(max_shots, 0)
+                shots = todo_shots
             else:
                 demh = be.DemHandle(dem, device=device)
                 dech = be.DecoderHandle(
@@ -173,23 +198,29 @@ class ThresholdLAB:
                 )
                 try:
                     shots, errors, discards = _run_task(
-                        dech, demh.tile_shots, seed + 1_000_003 * task_index, max_shots, max_errors,
-                        int(opts.get("batch_shots", 0)), dist, rank, world, device,
+                        dech, demh.tile_shots, seed + 1_000_003 * task_index, todo_shots, todo_errors,
+                        int(opts.get("batch_shots", 0)), dist, rank, world, device, shot0=shot0,
                     )
                 finally:
                     dech.close()
                     demh.close()
-            samples.append(
-                TaskStats(
-                    strong_id=task.strong_id(self.decoder),
-                    decoder=self.decoder,
-                    json_metadata=task.json_metadata,
-                    shots=shots,
-                    errors=errors,
-                    discards=discards,
-                    seconds=time.perf_counter() - t0,
-                )
+            new = TaskStats(
+                strong_id=strong_id,
+                decoder=self.decoder,
+                json_metadata=task.json_metadata,
+                shots=shots,
+                errors=errors,
+                discards=discards,
+                seconds=time.perf_counter() - t0,
             )
+            if save_resume_filepath and rank == 0 and shots > 0:
+                append_stats_to_csv(save_resume_filepath, new)
+            if before is not None:
+                new.shots += before.shots
+                new.errors += before.errors
+                new.discards += before.discards
+                new.seconds += before.seconds
+            samples.append(new)
         self._samples = samples
 
     # ------------------------------------------------------------------ plotting (A11, host only)
@@ -292,16 +323,20 @@ def _split_batch(shot0: int, nshots: int, tile: int, rank: int, world: int) -> t
 
 
 def _run_task(dech, tile: int, seed: int, max_shots: int, max_errors: int, batch_shots: int,
-              dist, rank: int, world: int, device: int) -> tuple[int, int, int]:
-    """Batches of shots until sinter's stop rule fires; returns global (shots, errors, discards)."""
+              dist, rank: int, world: int, device: int, shot0: int = 0) -> tuple[int, int, int]:
+    """Batches of shots until sinter's stop rule fires; returns global (shots, errors, discards).
+
+    ``shot0``: shots of this task's RNG stream already consumed by an earlier, recorded run (resume);
+    rounded up to a whole tile, the unit the counter-based sampler is keyed by."""
     shots = errors = discards = 0
+    base = -(-int(shot0) // tile) * tile
     # ramp the batch so that an early max_errors stop does not overshoot by much
     batch = batch_shots if batch_shots > 0 else 1 << 14
     batch = max(tile, batch - batch % tile)
     cap = batch_shots if batch_shots > 0 else (1 << 24) * world
     while shots < max_shots and (max_errors <= 0 or errors < max_errors):
         n = min(batch, max_shots - shots)
-        my0, myn = _split_batch(shots, n, tile, rank, world)
+        my0, myn = _split_batch(base + shots, n, tile, rank, world)
         # shot0 handed to the kernel must be tile aligned: ``shots`` only ever grows by whole
         # batches, and batches are multiples of the tile except for the very last one
         got = (0, 0, 0)

@@ -14,7 +14,8 @@ import json
 import math
 from dataclasses import dataclass, field
 
-__all__ = ["Task", "TaskStats", "AnonTaskStats", "wilson_interval", "CSV_HEADER"]
+__all__ = ["Task", "TaskStats", "AnonTaskStats", "wilson_interval", "CSV_HEADER",
+           "read_stats_from_csv", "append_stats_to_csv"]
 
 CSV_HEADER = "     shots,    errors,  discards, seconds,decoder,strong_id,json_metadata,custom_counts"
 
@@ -93,3 +94,54 @@ def wilson_interval(errors: int, shots: int, z: float = 1.959963984540054) -> tu
     centre = (phat + z * z / (2 * shots)) / denom
     half = z * math.sqrt(phat * (1 - phat) / shots + z * z / (4.0 * shots * shots)) / denom
     return (max(0.0, centre - half), min(1.0, centre + half))
+
+
+def read_stats_from_csv(path: str) -> list[TaskStats]:
+    """Rows of a CSV in sinter's schema, rows with one ``strong_id`` summed (what
+    ``sinter.read_stats_from_csv_files`` returns and what ``save_resume_filepath`` resumes from)."""
+    import csv
+    import os
+
+    merged: dict[str, TaskStats] = {}
+    if not os.path.exists(path):
+        return []
+    with open(path, newline="") as f:
+        rows = list(csv.reader(f, skipinitialspace=True))
+    if not rows:
+        return []
+    header = [h.strip() for h in rows[0]]
+    col = {name: header.index(name) for name in ("shots", "errors", "discards", "seconds", "decoder", "strong_id", "json_metadata")}
+    for row in rows[1:]:
+        if not row or len(row) <= col["json_metadata"]:
+            continue
+        sid = row[col["strong_id"]].strip()
+        meta_txt = row[col["json_metadata"]].strip()
+        inc = TaskStats(
+            strong_id=sid,
+            decoder=row[col["decoder"]].strip(),
+            json_metadata=json.loads(meta_txt) if meta_txt else None,
+            shots=int(row[col["shots"]]),
+            errors=int(row[col["errors"]]),
+            discards=int(row[col["discards"]]),
+            seconds=float(row[col["seconds"]]),
+        )
+        if sid in merged:
+            m = merged[sid]
+            m.shots += inc.shots
+            m.errors += inc.errors
+            m.discards += inc.discards
+            m.seconds += inc.seconds
+        else:
+            merged[sid] = inc
+    return list(merged.values())
+
+
+def append_stats_to_csv(path: str, stats: TaskStats) -> None:
+    """Append one row (writing the header first when the file is new or empty)."""
+    import os
+
+    new = not os.path.exists(path) or os.path.getsize(path) == 0
+    with open(path, "a") as f:
+        if new:
+            f.write(CSV_HEADER + "\n")
+        f.write(stats.to_csv_line() + "\n")

@@ -23,7 +23,7 @@ lib.hostsim_mt_stats(stats, 0)
 opred, owt = orc.decode_batch(dets, nthreads=8, return_weights=True)
 ok = rc == 0
 print("rc in {0,4}:", set(rc.tolist()) <= {0, 4}, "decoded", ok.sum(), "weights equal on those", (wt[ok] == owt[ok]).all(), "pred diff", (pred != opred[:, 0]).mean() if opred.ndim > 1 else (pred != opred).mean())
-names = ["events(search)", "stale pops", "grow", "shrink", "augment", "4:?", "scans", "expand", "free after start", "shots"] + ["s%d" % i for i in range(10, 16)]
+names = ["events(search)", "stale pops", "grow", "shrink", "augment", "4:?", "scans", "expand", "free after start", "shots", "-", "phases with 1 event", "phases with 2 events", "phases with 3 events", "phases with 4+ events", "augments ending at a free vertex"]
 shots = max(1, stats[9])
 for k, nm in enumerate(names):
     print("  %-20s %.3f per shot" % (nm, stats[k] / shots))

@@ -113,3 +113,55 @@ def test_curves_without_matplotlib():
     (name, xs, ys, lo, hi), = th.error_rate_curves("per_round")
     assert name == "A" and xs == [0.1]
     assert abs(ys[0] - (0.5 - 0.5 * (1 - 0.2) ** (1 / 3))) < 1e-12 and lo[0] < ys[0] < hi[0]
+
+
+def test_csv_roundtrip_in_sinter_schema(tmp_path):
+    from graphqec_b200.stats import CSV_HEADER, TaskStats, append_stats_to_csv, read_stats_from_csv
+    path = str(tmp_path / "stats.csv")
+    a = TaskStats("id-a", "pymatching", {"name": 'Rot "x"', "error": 0.001, "d": 5, "r": 5}, shots=1000, errors=7, seconds=1.5)
+    b = TaskStats("id-b", "pymatching", {"name": "B", "error": 0.002}, shots=10, errors=1)
+    append_stats_to_csv(path, a)
+    append_stats_to_csv(path, b)
+    append_stats_to_csv(path, TaskStats("id-a", "pymatching", a.json_metadata, shots=500, errors=3, discards=2, seconds=0.5))
+    lines = open(path).read().splitlines()
+    assert lines[0] == CSV_HEADER and len(lines) == 4
+    got = {s.strong_id: s for s in read_stats_from_csv(path)}
+    assert (got["id-a"].shots, got["id-a"].errors, got["id-a"].discards) == (1500, 10, 2)
+    assert got["id-a"].json_metadata == a.json_metadata and got["id-b"].shots == 10
+    assert read_stats_from_csv(str(tmp_path / "missing.csv")) == []
+
+
+def test_collect_stats_resumes_from_csv(tmp_path, monkeypatch):
+    """save_resume_filepath: recorded rows count towards the stop rule, new shots continue the RNG stream."""
+    from graphqec_b200 import backend as be
+    calls = []
+
+    class FakeDem:
+        tile_shots = 256
+        def __init__(self, dem, device=0): pass
+        def close(self): pass
+
+    class FakeDec(_FakeDecoder):
+        def __init__(self, demh, kind, **kw): pass
+        def collect(self, seed, shot0, nshots, max_errors):
+            calls.append((shot0, nshots))
+            return super().collect(seed, shot0, nshots, max_errors)
+        def close(self): pass
+
+    monkeypatch.setattr(be, "DemHandle", FakeDem)
+    monkeypatch.setattr(be, "DecoderHandle", FakeDec)
+    path = str(tmp_path / "resume.csv")
+    th = ThresholdLAB(configurations=[{"distance": 3}], code=RepetitionCode, error_rates=[0.05])
+    th.collect_stats(max_shots=20000, max_errors=0, save_resume_filepath=path)
+    assert th.samples[0].shots == 20000 and th.samples[0].errors == 20
+    first = list(calls)
+    calls.clear()
+    # same budget again: nothing left to do, the totals come from the file
+    th.collect_stats(max_shots=20000, max_errors=0, save_resume_filepath=path)
+    assert calls == [] and th.samples[0].shots == 20000
+    # a bigger budget continues behind the recorded shots (next whole tile)
+    th.collect_stats(max_shots=50000, max_errors=0, decoder_params={"save_resume_filepath": path})
+    assert calls[0][0] == -(-20000 // 256) * 256 and sum(n for _, n in calls) == 30000
+    assert th.samples[0].shots == 50000
+    assert len(open(path).read().splitlines()) == 3      # header + one row per run that did work
+    assert first[0][0] == 0
