@@ -13,7 +13,7 @@ from ctypes import POINTER, c_double, c_float, c_int, c_int32, c_uint8, c_uint32
 
 import numpy as np
 
-__all__ = ["load_library", "library_path", "DemHandle", "DecoderHandle", "GqError", "MATCHING", "BP_MINSUM"]
+__all__ = ["load_library", "library_path", "circuit_to_dem_arrays", "DemHandle", "DecoderHandle", "GqError", "MATCHING", "BP_MINSUM"]
 
 MATCHING = 1
 BP_MINSUM = 2
@@ -81,6 +81,10 @@ SIGNATURES = {
     "gq_last_timing": (c_int, [c_void_p, POINTER(c_double * 8)]),
     "gq_last_kernel_profile": (c_int, [c_void_p, POINTER(c_double * 4)]),
     "gq_sync": (c_int, [c_void_p]),
+    "gq_circuit_to_dem": (c_int, [ctypes.c_char_p, c_int, POINTER(c_void_p)]),
+    "gq_dem_build_sizes": (c_int, [c_void_p, POINTER(c_uint32 * 6)]),
+    "gq_dem_build_export": (c_int, [c_void_p] * 10),
+    "gq_dem_build_destroy": (None, [c_void_p]),
 }
 
 
@@ -108,6 +112,36 @@ def _check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load_library().gq_last_error()
         raise GqError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def circuit_to_dem_arrays(stim_text: str, decompose_errors: bool):
+    """Native circuit -> DEM (``gq_circuit_to_dem``, host code of the library, no device needed).
+
+    Returns ``(D, O, probs, det_indptr, det_idx, obs_indptr, obs_idx, comps)`` with ``comps`` =
+    ``(comp_indptr, comp_a, comp_b, comp_obs)`` or ``None``.  Raises ``ValueError`` with Stim's wording
+    when a mechanism cannot be decomposed (callers fall back to the undecomposed model like sinter)."""
+    lib = load_library()
+    h = c_void_p()
+    rc = lib.gq_circuit_to_dem(stim_text.encode(), 1 if decompose_errors else 0, ctypes.byref(h))
+    if rc != 0:
+        msg = lib.gq_last_error()
+        raise ValueError(msg.decode() if msg else f"gq_circuit_to_dem failed (code {rc})")
+    try:
+        sizes = (c_uint32 * 6)()
+        _check(lib.gq_dem_build_sizes(h, ctypes.byref(sizes)), "gq_dem_build_sizes")
+        D, O, M, nnz_h, nnz_l, ncomp = (int(x) for x in sizes)
+        probs = np.zeros(M, np.float64)
+        det_indptr = np.zeros(M + 1, np.uint32); det_idx = np.zeros(nnz_h, np.uint32)
+        obs_indptr = np.zeros(M + 1, np.uint32); obs_idx = np.zeros(nnz_l, np.uint32)
+        comps = None
+        if decompose_errors:
+            comps = (np.zeros(M + 1, np.uint32), np.zeros(ncomp, np.uint32), np.zeros(ncomp, np.uint32), np.zeros(ncomp, np.uint64))
+        ptrs = [_np_ptr(a) for a in (probs, det_indptr, det_idx, obs_indptr, obs_idx)]
+        ptrs += [_np_ptr(a) for a in comps] if comps else [None] * 4
+        _check(lib.gq_dem_build_export(h, *ptrs), "gq_dem_build_export")
+    finally:
+        lib.gq_dem_build_destroy(h)
+    return D, O, probs, det_indptr, det_idx, obs_indptr, obs_idx, comps
 
 
 def _np_ptr(a: np.ndarray | None):

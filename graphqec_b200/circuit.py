@@ -283,9 +283,18 @@ class Circuit:
         approximate_disjoint_errors: bool = True,
         **_ignored,
     ):
-        """Circuit -> DEM, the restatement of Stim's error analysis."""
-        from graphqec_b200.dem import circuit_to_dem
+        """Circuit -> DEM, the restatement of Stim's error analysis.
 
+        Built by the library's native builder (``gq_circuit_to_dem``) when ``libgqec_b200.so`` is present,
+        else by the equivalent Python one (``dem.circuit_to_dem``); both are host-side set-up and give
+        identical arrays (``tests/test_dem.py``).  ``GQEC_PY_DEM=1`` forces the Python builder."""
+        import os
+
+        from graphqec_b200 import backend
+        from graphqec_b200.dem import circuit_to_dem, circuit_to_dem_native
+
+        if os.environ.get("GQEC_PY_DEM") != "1" and os.path.exists(backend.library_path()):
+            return circuit_to_dem_native(self, decompose_errors=decompose_errors)
         return circuit_to_dem(self, decompose_errors=decompose_errors)
 
     def to_stim(self):

@@ -23,7 +23,7 @@ import numpy as np
 
 from graphqec_b200.circuit import Circuit, GateTarget
 
-__all__ = ["DetectorErrorModel", "circuit_to_dem", "depolarize1_component", "depolarize2_component"]
+__all__ = ["DetectorErrorModel", "circuit_to_dem", "circuit_to_dem_native", "depolarize1_component", "depolarize2_component"]
 
 NO_DET = 0xFFFFFFFF
 
@@ -108,6 +108,36 @@ class DetectorErrorModel:
         self.comp_a = np.array([c[0] for c in flat], dtype=np.uint32)
         self.comp_b = np.array([c[1] for c in flat], dtype=np.uint32)
         self.comp_obs = np.array([c[2] for c in flat], dtype=np.uint64)
+
+    @classmethod
+    def from_arrays(cls, num_detectors, num_observables, probs, det_indptr, det_idx, obs_indptr, obs_idx,
+                    comps=None) -> "DetectorErrorModel":
+        """Adopt CSR arrays as they are (the native builder's output, ``gq_circuit_to_dem``)."""
+        self = cls.__new__(cls)
+        self.num_detectors = int(num_detectors)
+        self.num_observables = int(num_observables)
+        self.probs = np.ascontiguousarray(probs, dtype=np.float64)
+        self.det_indptr = np.ascontiguousarray(det_indptr, dtype=np.uint32)
+        self.det_idx = np.ascontiguousarray(det_idx, dtype=np.uint32)
+        self.obs_indptr = np.ascontiguousarray(obs_indptr, dtype=np.uint32)
+        self.obs_idx = np.ascontiguousarray(obs_idx, dtype=np.uint32)
+        self.decomposed = comps is not None
+        if comps is None:
+            # every mechanism is its own piece when it is graphlike (<= 2 detectors), else none
+            m = self.probs.shape[0]
+            sizes = np.diff(self.det_indptr.astype(np.int64))
+            first = self.det_idx[np.minimum(self.det_indptr[:-1], max(self.det_idx.size - 1, 0))] if self.det_idx.size else np.zeros(m, np.uint32)
+            second = self.det_idx[np.minimum(self.det_indptr[:-1] + 1, max(self.det_idx.size - 1, 0))] if self.det_idx.size else np.zeros(m, np.uint32)
+            a = np.where((sizes == 1) | (sizes == 2), first, NO_DET).astype(np.uint32)
+            b = np.where(sizes == 2, second, NO_DET).astype(np.uint32)
+            omask = np.zeros(m, np.uint64)
+            rows = np.repeat(np.arange(m), np.diff(self.obs_indptr.astype(np.int64)))
+            np.bitwise_xor.at(omask, rows, np.uint64(1) << self.obs_idx.astype(np.uint64))
+            comps = (np.arange(m + 1, dtype=np.uint32), a, b, omask)
+        self.comp_indptr, self.comp_a, self.comp_b, self.comp_obs = (
+            np.ascontiguousarray(comps[0], np.uint32), np.ascontiguousarray(comps[1], np.uint32),
+            np.ascontiguousarray(comps[2], np.uint32), np.ascontiguousarray(comps[3], np.uint64))
+        return self
 
     # ------------------------------------------------------------------ helpers
     def _self_component(self, i: int) -> tuple[int, int, int]:
@@ -450,6 +480,14 @@ def _decompose(
 
     rec(dets, [])
     return best
+
+
+def circuit_to_dem_native(circuit: Circuit, decompose_errors: bool = False) -> DetectorErrorModel:
+    """The same model as ``circuit_to_dem`` from the library's native builder (``gq_circuit_to_dem``,
+    csrc/circuit_dem.cu: host C++, ~50x faster on a d = 11 memory circuit); bit-identical arrays."""
+    from graphqec_b200 import backend
+
+    return DetectorErrorModel.from_arrays(*backend.circuit_to_dem_arrays(str(circuit), decompose_errors))
 
 
 def circuit_to_dem(circuit: Circuit, decompose_errors: bool = False) -> DetectorErrorModel:

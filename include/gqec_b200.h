@@ -88,6 +88,26 @@ int gq_dem_create(uint32_t num_detectors, uint32_t num_observables, uint32_t num
 void gq_dem_destroy(gq_dem *dem);
 int gq_dem_get_info(const gq_dem *dem, gq_dem_info *info);
 
+/* ---- circuit -> DEM, native host code (no device needed): replaces UPSTREAM
+ *      stim.Circuit.detector_error_model(decompose_errors=..., approximate_disjoint_errors=True), which
+ *      sinter calls for every task because the reference's Tasks carry no DEM
+ *      (reference graphqec/lab/threshold/threshold_lab.py:151).
+ *      stim_text: the circuit in Stim's text syntax (str(circuit); REPEAT blocks are unrolled); gate set
+ *      R RX M MX MR MRX H X Y Z I S S_DAG CX CZ SWAP DEPOLARIZE1/2 X/Y/Z_ERROR DETECTOR
+ *      OBSERVABLE_INCLUDE TICK QUBIT_COORDS SHIFT_COORDS.  Mechanisms come out sorted by (detector
+ *      tuple, observable mask), equal symptoms merged.  decompose_errors != 0 also yields the graphlike
+ *      pieces of every mechanism (GQ_E_UNSUPPORTED when one cannot be split -- sinter then falls back to
+ *      the undecomposed model).  Export into caller-owned arrays sized from gq_dem_build_sizes:
+ *      sizes = {D, O, M, nnz(H), nnz(L), number of pieces}; the comp_* arrays may be NULL when the model
+ *      was built without decomposition.  The arrays are exactly gq_dem_create's inputs. */
+typedef struct gq_dem_build gq_dem_build;
+int gq_circuit_to_dem(const char *stim_text, int decompose_errors, gq_dem_build **out);
+int gq_dem_build_sizes(const gq_dem_build *b, uint32_t sizes[6]);
+int gq_dem_build_export(const gq_dem_build *b, double *p, uint32_t *det_indptr, uint32_t *det_idx,
+                        uint32_t *obs_indptr, uint32_t *obs_idx, uint32_t *comp_indptr,
+                        uint32_t *comp_a, uint32_t *comp_b, uint64_t *comp_obs);
+void gq_dem_build_destroy(gq_dem_build *b);
+
 /* ---- sampling + extraction: replaces
  *      circuit.compile_detector_sampler().sample(shots, bit_packed=True, separate_observables=True)
  *      (SURVEY.md 8a row A7).  Counter-based Philox4x32-10 keyed by (seed, global tile index,

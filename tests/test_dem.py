@@ -133,3 +133,61 @@ def test_dem_text_repeat_and_shift():
     dem = DetectorErrorModel.from_text(txt)
     assert dem.num_errors == 4 and dem.num_detectors == 3
     assert [dem.mechanism(i)[1] for i in range(4)] == [(0,), (0, 1), (1, 2), (2,)]
+
+
+# ------------------------------------------------------------------------------------------
+# native builder (gq_circuit_to_dem, csrc/circuit_dem.cu) == Python builder, array for array
+# ------------------------------------------------------------------------------------------
+
+def _native_cases():
+    from graphqec_b200 import BivariateBicycleCode
+    steane = np.array([[1, 1, 1, 1, 0, 0, 0], [0, 1, 1, 0, 1, 1, 0], [0, 0, 1, 1, 0, 1, 1]])
+    return [
+        ("rep5", RepetitionCode(distance=5, depolarize1_rate=0.1, depolarize2_rate=0.1), 5, "Z"),
+        ("rot5z", RotatedSurfaceCode(distance=5, depolarize1_rate=0.005, depolarize2_rate=0.005), 5, "Z"),
+        ("rot5x", RotatedSurfaceCode(distance=5, depolarize1_rate=0.005, depolarize2_rate=0.003), 4, "X"),
+        ("rot4_even", RotatedSurfaceCode(distance=4, depolarize1_rate=0.01, depolarize2_rate=0.01), 4, "Z"),
+        ("unrot3", UnrotatedSurfaceCode(distance=3, depolarize1_rate=0.003, depolarize2_rate=0.007), 3, "Z"),
+        ("steane", CssCode(Hx=steane, Hz=steane, depolarize1_rate=0.002, depolarize2_rate=0.002), 3, "Z"),
+        ("bb72", BivariateBicycleCode(L1=6, L2=6, a1=3, a2=1, a3=2, b1=3, b2=1, b3=2,
+                                      depolarize1_rate=0.001, depolarize2_rate=0.001), 2, "Z"),
+    ]
+
+
+@pytest.mark.parametrize("case", _native_cases(), ids=lambda c: c[0])
+def test_native_builder_equals_python_builder(case):
+    from graphqec_b200.dem import circuit_to_dem, circuit_to_dem_native
+    _, code, rounds, lc = case
+    code.build_memory_circuit(number_of_rounds=rounds, logic_check=lc)
+    circ = code.memory_circuit
+    for decompose in (False, True):
+        try:
+            want = circuit_to_dem(circ, decompose)
+        except ValueError as exc:
+            with pytest.raises(ValueError) as got:
+                circuit_to_dem_native(circ, decompose)
+            assert str(got.value) == str(exc)      # same first undecomposable mechanism, same wording
+            continue
+        got = circuit_to_dem_native(circ, decompose)
+        assert (got.num_detectors, got.num_observables, got.decomposed) == (want.num_detectors, want.num_observables, want.decomposed)
+        for f in ("probs", "det_indptr", "det_idx", "obs_indptr", "obs_idx", "comp_indptr", "comp_a", "comp_b", "comp_obs"):
+            a, b = getattr(want, f), getattr(got, f)
+            assert a.dtype == b.dtype and a.shape == b.shape and (a == b).all(), f    # probabilities bit for bit
+        assert str(got) == str(want)
+
+
+def test_native_builder_text_front_end():
+    from graphqec_b200 import backend
+    from graphqec_b200.circuit import Circuit
+    from graphqec_b200.dem import circuit_to_dem
+    body = "CNOT 0 1 1 2\nDEPOLARIZE2(0.01) 0 1 1 2  # hook\nMR(0.002) 1\nDETECTOR rec[-1] rec[-2]\n"
+    flat = "R 0 1 2\nMR 1\n" + body * 3 + "M 0 2\nOBSERVABLE_INCLUDE(0) rec[-1]\n"
+    looped = "R 0 1 2\nMR 1\nREPEAT 3 {\n" + "".join("    " + l + "\n" for l in body.splitlines()) + "}\nM 0 2\nOBSERVABLE_INCLUDE(0) rec[-1]\n"
+    want = circuit_to_dem(Circuit(flat), False)
+    for text in (flat, looped):
+        D, O, p, dp, di, op_, oi, comps = backend.circuit_to_dem_arrays(text, False)
+        assert (D, O) == (3, 1) and comps is None
+        assert (p == want.probs).all() and (di == want.det_idx).all() and (oi == want.obs_idx).all()
+    for bad in ("FOO 1", "CX 0", "DETECTOR rec[-1]", "M 0\nDETECTOR 0", "REPEAT 2 {\nM 0\n"):
+        with pytest.raises(ValueError):
+            backend.circuit_to_dem_arrays(bad, False)
