@@ -190,7 +190,11 @@ class DemHandle:
             load_library().gq_dem_destroy(self._h)
             self._h = c_void_p()
 
-    __del__ = close
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: module globals are already gone
+            pass
 
     # ---- helpers
     def _dev(self):
@@ -280,7 +284,11 @@ class DecoderHandle:
             load_library().gq_decoder_destroy(self._h)
             self._h = c_void_p()
 
-    __del__ = close
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: module globals are already gone
+            pass
 
     def edges(self):
         """-> (u, v [NO_DET = boundary], integer weight, observable mask, merged probability)"""

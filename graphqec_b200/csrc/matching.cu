@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
 #define GQ_SIDE_STREAMS 0   // 1: the smaller classes' kernels run on side streams (overlapping tails, but co-resident
                             // kernels share the instruction cache: measured slower once start/solve were split)
 #endif
-static constexpr int MT_CLASSES = 6;     // K = 1 .. 6
+static constexpr int MT_CLASSES = 8;     // K = 1 .. 8 (the event keys hold the vertex in 8 bits: 256 defects is the limit)
 static constexpr int MT_CAP = 32 * MT_CLASSES;
 
 template <int K>
@@ -409,7 +409,7 @@ struct StartWarpMem {
 };
 
 template <int K>
-__global__ void __launch_bounds__(256, 8) tree_start_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(256, (K <= 4 ? 8 : (K <= 6 ? 4 : 3))) tree_start_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256, 8) tree_start_kernel(MatchArgs a) {
 // throughput instantiation leaves that code out, which is worth it because the kernel is at the edge of
 // the instruction cache
 template <int K, bool EXTRAS>
-__global__ void __launch_bounds__(256, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : 2))) tree_solve_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(256, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? 2 : 1)))) tree_solve_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -509,7 +509,7 @@ static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, i
     const int blocks_a = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * 8);   // latency-bound: all 64 warps/SM
     tree_start_kernel<K><<<blocks_a, 256, 8 * sizeof(StartWarpMem<K>), st>>>(b);
     if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
-    const int per_sm = K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : 2);
+    const int per_sm = K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? 2 : 1));
     const int blocks_b = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * per_sm);
     if (ev0) cudaEventRecord(ev0, st);   // bench.py's roofline times the solve kernel of the biggest class
     if (b.weight_out || b.flags_out || b.corr_out) tree_solve_kernel<K, true><<<blocks_b, 256, 8 * sizeof(MtWarpMem<K>), st>>>(b);
@@ -535,7 +535,9 @@ static size_t start_record_bytes(int c) {   // class c = K - 1
     case 2: return sizeof(StartRecord<3>);
     case 3: return sizeof(StartRecord<4>);
     case 4: return sizeof(StartRecord<5>);
-    default: return sizeof(StartRecord<6>);
+    case 5: return sizeof(StartRecord<6>);
+    case 6: return sizeof(StartRecord<7>);
+    default: return sizeof(StartRecord<8>);
     }
 }
 
@@ -744,10 +746,10 @@ int gq_matching_create(gq_dec *dec) {
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     if (configure_tree_class<1>() || configure_tree_class<2>() || configure_tree_class<3>() || configure_tree_class<4>() ||
-        configure_tree_class<5>() || configure_tree_class<6>())
+        configure_tree_class<5>() || configure_tree_class<6>() || configure_tree_class<7>() || configure_tree_class<8>())
         GQ_FAIL(GQ_E_CUDA, "matching decoder: cudaFuncSetAttribute failed for the first-tier kernels");
     GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << GQ_SLICE_LOG2) + 16) * 4));
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < MT_CLASSES - 1; ++i) {
         GQ_CUDA(cudaStreamCreateWithFlags(&dec->side_streams[i], cudaStreamNonBlocking));
         GQ_CUDA(cudaEventCreateWithFlags(&dec->side_done[i], cudaEventDisableTiming));
     }
@@ -769,7 +771,7 @@ void gq_matching_destroy(gq_dec *dec) {
     cudaFree(dec->d_dist); cudaFree(dec->d_pobs); cudaFree(dec->d_next); cudaFree(dec->d_nbr);
     cudaFree(dec->d_adj_ptr); cudaFree(dec->d_adj_node); cudaFree(dec->d_adj_edge);
     cudaFree(dec->d_ws_fast); cudaFree(dec->d_ws_big); cudaFree(dec->d_overflow); cudaFree(dec->d_lists); cudaFree(dec->d_recs);
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < MT_CLASSES - 1; ++i) {
         if (dec->side_streams[i]) cudaStreamDestroy(dec->side_streams[i]);
         if (dec->side_done[i]) cudaEventDestroy(dec->side_done[i]);
     }
@@ -853,7 +855,9 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
                 case 2: lrc = launch_tree_class<3>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 case 3: lrc = launch_tree_class<4>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 case 4: lrc = launch_tree_class<5>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                default: lrc = launch_tree_class<6>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 5: lrc = launch_tree_class<6>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 6: lrc = launch_tree_class<7>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                default: lrc = launch_tree_class<8>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 }
                 if (lrc) GQ_FAIL(lrc, "matching decoder: first-tier kernel launch failed");
                 if (st != dem->stream) {

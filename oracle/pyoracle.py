@@ -121,9 +121,12 @@ class MwpmOracle:
         self._h = lib().orc_graph_create(self.nd, self.no, len(edges), _p(eu), _p(ev), _p(self.weights), _p(eo))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_graph_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().orc_graph_free(self._h)
+                self._h = None
+        except Exception:   # interpreter shutdown
+            pass
 
     def dist_table(self) -> np.ndarray:
         n = self.nd
