@@ -41,6 +41,17 @@ NCU_WARP_INSTR_PER_SHOT = 4198034323 / 767034
 NCU_ISSUE_ACTIVE_PCT = 70.2
 
 
+_JSON_FD = None
+
+
+def emit_json(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def north_star_dem():
     from graphqec_b200 import RotatedSurfaceCode
 
@@ -175,7 +186,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def main():
@@ -189,6 +200,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # stdout carries exactly one JSON line: everything libraries print there (NCCL's version banner, ...) is
+    # sent to stderr, and the line itself is written to the saved descriptor
+    sys.stdout.flush()
+    global _JSON_FD
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -340,7 +357,7 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
