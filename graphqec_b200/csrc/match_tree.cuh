@@ -227,20 +227,104 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
             bool have_masks = false; // nm[] may hold vertices (set by the blossom events only)
             bool inner_blossoms = false;   // an inner (T) top-level blossom exists in this tree
             {
-                // the root turns outer: its key bits and boundary event are formed once (warp-uniform slot)
+                // ---- the root's row, scanned once.  At the start of a phase every vertex is unlabelled, so the
+                // offers are plain "reach" events (type 0) and the root's own boundary event.  When the earliest of
+                // them ends the phase at once -- the boundary, a free vertex or a vertex that sits on the boundary
+                // (a third of all phases at the north star) -- the match and the root's dual are written directly
+                // and no tree is set up; otherwise the offers become the tree's first event keys.
                 const bool mine = lane == (root & (GQW_LANES - 1));
-                const i32 rb4 = (i32)sel_slot<K>(b4, rk), ryb = (i32)sel_slot<K>(yb, rk);
+                i32 rb4, ryb;
+                GQT_SEL(b4, root, rb4);
+                GQT_SEL(yb, root, ryb);
                 const unsigned rbk = rb4 < SL_INF ? (((unsigned)(rb4 - ryb) << 10) | 0x300u | (unsigned)root) : 0xffffffffu;
+                const uint32_t ro = (uint32_t)def[root] * N;
+                unsigned best0 = rbk;
+                GQM_STAT(6, 1);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    ek[k] = EK_NONE; slfrom[k] = -1;
+                    const i32 wt = (i32)dist[ro + dj[k]];      // the diagonal is infinite: the root offers nothing to itself
+                    const i32 x = 4 * wt - ryb - yb[k];
+                    ek[k] = wt != (i32)W_INF ? (((unsigned)x << 10) + kb[k]) : EK_NONE;
+                    best0 = min(best0, ek[k]);
+                }
+                best0 = __reduce_min_sync(GQW_FULL, best0);
+                if (best0 < 0x7ffffc00u) {
+                    const int v0 = best0 & 0xff;
+                    int done = 0;
+                    if (((best0 >> 8) & 3) == 3) {
+                        if (lane == 0) f.mate[root] = -2;
+                        done = 1;
+                    } else if (f.top[v0] == v0 && f.mate[v0] < 0) {
+                        if (lane == 0) { f.mate[root] = (i16)v0; f.mate[v0] = (i16)root; }
+                        done = 1;
+                    }
+                    if (done) {
+                        GQM_STAT(0, 1); GQM_STAT(4, 1); GQM_STAT(11, 1);
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+                            if (mine && k == rk) yb[k] += (i32)(best0 >> 10);
+                        __syncwarp();
+                        continue;
+                    }
+                    // ---- one step further (another 40 % of the phases): the root reaches a plain vertex v0 matched
+                    // to a plain vertex w0 at clock t1; w0 turns outer and offers its row.  If the next event is an
+                    // augmentation -- the root or w0 reaches the boundary, a free vertex or a vertex sitting on the
+                    // boundary -- the two or three new mates and duals are written directly.  Candidates, with the
+                    // source in the type bits: 0 root -> k (the offers above), 1 w0 -> k, 2 the edge root - w0 turning
+                    // tight (a blossom: left to the tree code), 3 boundary of root / w0.
+                    const int w0 = f.top[v0] == v0 ? (int)f.mate[v0] : -1;
+                    if (((best0 >> 8) & 3) == 0 && w0 >= 0 && f.top[w0] == w0) {
+                        const i32 t1 = (i32)(best0 >> 10);
+                        i32 yw, wb4;
+                        GQT_SEL(yb, w0, yw);
+                        GQT_SEL(b4, w0, wb4);
+                        const uint32_t rw = (uint32_t)def[w0] * N;
+                        const i32 ew = t1 - yw;          // w0 reaches k at clock 4 d(w0, k) - y_k + ew
+                        unsigned b2 = rbk;
+                        if (wb4 < SL_INF) b2 = min(b2, ((unsigned)(wb4 + ew) << 10) | 0x300u | (unsigned)w0);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const int x = lane + GQW_LANES * k;
+                            const i32 wt = (i32)dist[rw + dj[k]];
+                            unsigned c = ek[k];
+                            if (x == v0) c = 0xffffffffu;
+                            if (x == w0) c = ek_has(ek[k]) ? (((unsigned)((ek_time(ek[k]) + t1) >> 1) << 10) | 0x200u | (unsigned)x) : 0xffffffffu;
+                            const unsigned c2 = (wt != (i32)W_INF && x != v0 && x != root)
+                                                    ? ((((unsigned)(4 * wt - yb[k] + ew)) << 10) | 0x100u | (unsigned)x) : 0xffffffffu;
+                            b2 = min(b2, min(c, c2));
+                        }
+                        b2 = __reduce_min_sync(GQW_FULL, b2);
+                        const int ty = (b2 >> 8) & 3, k2 = b2 & 0xff;
+                        if (b2 < 0x7ffffc00u && ty != 2 && (ty == 3 || (f.top[k2] == k2 && f.mate[k2] < 0))) {
+                            GQM_STAT(0, 2); GQM_STAT(2, 1); GQM_STAT(4, 1); GQM_STAT(6, 1); GQM_STAT(12, 1);
+                            const bool from_root = ty == 0 || (ty == 3 && k2 == root);
+                            if (lane == 0) {
+                                const int src = from_root ? root : w0;
+                                if (!from_root) { f.mate[root] = (i16)v0; f.mate[v0] = (i16)root; }
+                                if (ty == 3) f.mate[src] = -2;
+                                else { f.mate[src] = (i16)k2; f.mate[k2] = (i16)src; }
+                            }
+                            const i32 t2 = (i32)(b2 >> 10), dt = t2 - t1;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const int x = lane + GQW_LANES * k;
+                                yb[k] += x == root ? t2 : (x == w0 ? dt : (x == v0 ? -dt : 0));
+                            }
+                            __syncwarp();
+                            continue;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    slfrom[k] = ek[k] != EK_NONE ? root : -1;
                     if (mine && k == rk) { kb[k] = (unsigned)root | KB_OUTER; bk[k] = rbk; }
                 }
                 if (mine) f.label[root] = L_S;
             }
 #pragma unroll
             for (int k = 0; k < K; ++k) nm[k] = 0u;
-            sv = root;
+            sv = -1;
             __syncwarp();
             int fail = 0;
             int guard = 8 * (cap + FT::nb) + 64;   // bounds the blossom events of a phase (grow steps are bounded by n)

@@ -77,3 +77,36 @@ def test_bposd_name_runs_min_sum_bp():
     th.collect_stats(max_shots=20000, max_errors=10**9)
     st = th.samples[0]
     assert st.shots == 20000 and st.errors < 2000
+
+
+def test_x_memory_point_inside_oracle_interval():
+    """logic_check="X" (three of the reference's notebooks run X-memory experiments)."""
+    th = ThresholdLAB(configurations=[{"distance": 5}], code=RotatedSurfaceCode, error_rates=[0.008], logic_check="X")
+    th.collect_stats(max_shots=200_000, max_errors=10**9, logic_check="X")
+    st = th.samples[0]
+    assert st.shots == 200_000 and st.json_metadata["d"] == 5
+    code = RotatedSurfaceCode(distance=5, depolarize1_rate=0.008, depolarize2_rate=0.008)
+    code.build_memory_circuit(number_of_rounds=5, logic_check="X")
+    dem = code.memory_circuit.detector_error_model(decompose_errors=True)
+    n, e = po.collect(dem, seed=6, nshots=100_000, nthreads=8)
+    lo, hi = po.wilson(e, n)
+    glo, ghi = wilson_interval(st.errors, st.shots)
+    assert glo <= hi and lo <= ghi
+
+
+def test_collect_stats_resume_on_the_device(tmp_path):
+    """save_resume_filepath through the real backend: a second call with the same budget does no work, a bigger
+    budget adds exactly the difference, and the CSV totals equal the samples."""
+    from graphqec_b200.stats import read_stats_from_csv
+    path = str(tmp_path / "sweep.csv")
+    th = ThresholdLAB(configurations=[{"distance": 3}], code=RotatedSurfaceCode, error_rates=[0.004, 0.008])
+    th.collect_stats(max_shots=50_000, max_errors=10**9, save_resume_filepath=path)
+    first = [(s.shots, s.errors) for s in th.samples]
+    th.collect_stats(max_shots=50_000, max_errors=10**9, save_resume_filepath=path)
+    assert [(s.shots, s.errors) for s in th.samples] == first
+    th.collect_stats(max_shots=120_000, max_errors=10**9, save_resume_filepath=path)
+    assert [s.shots for s in th.samples] == [120_000, 120_000]
+    rows = {s.strong_id: s for s in read_stats_from_csv(path)}
+    for s in th.samples:
+        assert (rows[s.strong_id].shots, rows[s.strong_id].errors) == (s.shots, s.errors)
+        assert s.errors > first[0][1] // 2
