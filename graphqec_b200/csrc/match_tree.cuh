@@ -689,27 +689,21 @@ __device__ __forceinline__ int solve_predict(const Tables &T, FT &f, const u16 *
     uint32_t pm = 0;
     int wt = 0, bad = 0;
     if (rc == 0) {
-        const uint8_t *bobs = T.pobs + (size_t)bro;
+        // one gather per slot, no divergent branches: the boundary is row D of the path-observable table
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int v = lane + GQW_LANES * k;
-            if (v < n) {
-                const int j = f.mate[v];
-                if (j == -2) {
-                    if (b4[k] == SL_INF) bad = 1;
-                    pm ^= bobs[dj[k]];
-                    wt += b4[k] >> 2;
-                } else if (j < 0) {
-                    bad = 1;
-                } else if (j > v) {
-                    const uint32_t at = (uint32_t)def[j] * N + dj[k];
-                    pm ^= T.pobs[at];
-                    if (want_weight) {
-                        const uint32_t d = dist[at];
-                        if (d >= (uint32_t)W_INF) bad = 1;
-                        wt += (int)d;
-                    }
-                }
+            const int j = v < n ? (int)f.mate[v] : -3;
+            const bool onb = j == -2, pair = j > v;     // a pair is counted by its lower end
+            bad |= (j == -1) | (onb & (b4[k] == SL_INF));
+            const uint32_t prow = onb ? T.D : (uint32_t)def[pair ? j : 0];
+            const uint32_t at = prow * N + dj[k];
+            if (onb | pair) pm ^= T.pobs[at];
+            if (onb) wt += b4[k] >> 2;
+            if (want_weight && pair) {
+                const uint32_t d = dist[at];
+                if (d >= (uint32_t)W_INF) bad = 1;
+                wt += (int)d;
             }
         }
         pm = __reduce_xor_sync(GQW_FULL, pm);
