@@ -36,4 +36,4 @@ for lo, hi in ((33, 64), (65, 96), (97, 128)):
     to._tree_decode(lib, orc, dets[sel])
     lib.hostsim_mt_stats(stats, 0)
     s = max(1, stats[9])
-    print(f"class {lo}..{hi}: {sel.sum()} shots, mean n {nd[sel].mean():.1f}: " + ", ".join(f"{nm} {stats[k]/s:.2f}" for k, nm in enumerate(names[:9])))
+    print(f"class {lo}..{hi}: {sel.sum()} shots, mean n {nd[sel].mean():.1f}: " + ", ".join(f"{nm} {stats[k]/s:.2f}" for k, nm in enumerate(names[:16]) if nm != "-"))
