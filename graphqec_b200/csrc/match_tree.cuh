@@ -132,6 +132,21 @@ __device__ __forceinline__ int sel_slot(const TV (&arr)[K], const int slot) {
             }
             return (slot & 4) ? hi : lo;
         }
+    } else if constexpr (K <= 16) {
+        // two halves of (up to) eight, each a select tree
+        int lo, hi;
+        {
+            const int a0 = (slot & 2) ? ((slot & 1) ? (int)arr[3] : (int)arr[2]) : ((slot & 1) ? (int)arr[1] : (int)arr[0]);
+            const int a1 = (slot & 2) ? ((slot & 1) ? (int)arr[7] : (int)arr[6]) : ((slot & 1) ? (int)arr[5] : (int)arr[4]);
+            lo = (slot & 4) ? a1 : a0;
+        }
+        {
+            auto at = [&](int i) -> int { return i < K ? (int)arr[i < K ? i : 0] : 0; };
+            const int b0 = (slot & 2) ? ((slot & 1) ? at(11) : at(10)) : ((slot & 1) ? at(9) : at(8));
+            const int b1 = (slot & 2) ? ((slot & 1) ? at(15) : at(14)) : ((slot & 1) ? at(13) : at(12));
+            hi = (slot & 4) ? b1 : b0;
+        }
+        return (slot & 8) ? hi : lo;
     } else return (int)arr[slot];
 }
 
@@ -142,19 +157,28 @@ __device__ __forceinline__ int sel_slot(const TV (&arr)[K], const int slot) {
 // exhausted, 3 step guard.
 //
 // Per-slot event keys (one register each, so the search is a handful of integer minima):
-//   ek = pending edge event  : time << 10 | type << 8 | vertex   (type 0: an outer vertex reaches this
+//   ek = pending edge event  : time << TS | type << VB | vertex   (type 0: an outer vertex reaches this
 //        unlabelled vertex, 1: outer-outer edge turns tight); an inner vertex keeps its frozen slack
 //        in the same layout with bit 31 set, which also keeps it out of the search
-//   bk = boundary event of an outer vertex: time << 10 | 3 << 8 | vertex
+//   bk = boundary event of an outer vertex: time << TS | 3 << VB | vertex
 // Label of a slot = the key bits it contributes: kb = vertex (unlabelled), vertex | 0x100 (outer),
 // vertex | bit 31 (inner).  With X = 4w - y_u + (D - yb[k]) the candidate time of an edge from outer u
 // is X for unlabelled and inner targets (time resp. frozen slack) and X / 2 for outer ones.
+// Field widths: the vertex takes VB = 8 bits up to 256 defects per shot and 9 bits beyond (up to 512), the
+// type 2 bits above it, the time the rest below bit 31 (21 resp. 20 bits; times stay below 2^20: they are
+// bounded by 8 x the largest table distance, a u16).
 static const unsigned EK_NONE = 0x7fffffffu;   // no pending edge event (time field all ones)
 static const unsigned EK_FROZEN = 0x80000000u;
-static const unsigned KB_OUTER = 0x100u;
+template <int K> struct KeyBits {
+    static constexpr int VB = (K * GQW_LANES > 256) ? 9 : 8;
+    static constexpr int TS = VB + 2;
+    static constexpr unsigned VM = (1u << VB) - 1u;
+    static constexpr unsigned TY1 = 1u << VB, TY2 = 2u << VB, TY3 = 3u << VB;
+    static constexpr unsigned LIM = (EK_NONE >> TS) << TS;     // keys at or above this hold no event
+};
 
-__device__ __forceinline__ bool ek_has(unsigned ek) { return (ek | 0x800003ffu) != 0xffffffffu; }
-__device__ __forceinline__ i32 ek_time(unsigned ek) { return (i32)((ek >> 10) & 0x1fffffu); }
+template <int TS> __device__ __forceinline__ bool ek_has(unsigned ek) { return (ek | 0x80000000u | ((1u << TS) - 1u)) != 0xffffffffu; }
+template <int TS> __device__ __forceinline__ i32 ek_time(unsigned ek) { return (i32)((ek >> TS) & ((1u << (31 - TS)) - 1u)); }
 
 template <int K, class FT>
 __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, const uint32_t N,
@@ -162,6 +186,8 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                                           const uint32_t (&dj)[K], const i32 (&b4)[K], i32 (&yb)[K],
                                           gqw_mask freebits) {
     constexpr int cap = FT::cap;
+    constexpr int VB = KeyBits<K>::VB, TS = KeyBits<K>::TS;
+    constexpr unsigned VM = KeyBits<K>::VM, TY1 = KeyBits<K>::TY1, TY2 = KeyBits<K>::TY2, TY3 = KeyBits<K>::TY3, KB_OUTER = TY1, EK_LIM = KeyBits<K>::LIM;
     unsigned ek[K], bk[K], kb[K];
     int slfrom[K], vtop[K];
     i32 D = 0;
@@ -174,7 +200,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
 #define GQT_MAKE_OUTER(k_)                                                                      \
     {                                                                                           \
         kb[k_] = (unsigned)(lane + GQW_LANES * (k_)) | KB_OUTER;                                \
-        bk[k_] = b4[k_] < SL_INF ? (((unsigned)(b4[k_] - yb[k_]) << 10) | 0x300u | (unsigned)(lane + GQW_LANES * (k_))) : 0xffffffffu; \
+        bk[k_] = b4[k_] < SL_INF ? (((unsigned)(b4[k_] - yb[k_]) << TS) | TY3 | (unsigned)(lane + GQW_LANES * (k_))) : 0xffffffffu; \
     }
 // scan the row of outer vertex u_ (its dual is yb + D): offer its edges to every vertex of other nodes
 #define GQT_SCAN(u_)                                                                            \
@@ -188,7 +214,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
         _Pragma("unroll") for (int k_ = 0; k_ < K; ++k_) {                                      \
             const i32 wt_ = (i32)dist[ro_ + dj[k_]];                                            \
             const i32 x_ = 4 * wt_ + (e0_ - yb[k_]);                                            \
-            const unsigned nk_ = ((unsigned)(x_ >> ((kb[k_] >> 8) & 1u)) << 10) + kb[k_];       \
+            const unsigned nk_ = ((unsigned)(x_ >> ((kb[k_] >> VB) & 1u)) << TS) + kb[k_];       \
             const bool up_ = wt_ != (i32)W_INF && vtop[k_] != tu_ && nk_ < ek[k_];              \
             ek[k_] = up_ ? nk_ : ek[k_];                                                        \
             slfrom[k_] = up_ ? su_ : slfrom[k_];                                                \
@@ -236,7 +262,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                 i32 rb4, ryb;
                 GQT_SEL(b4, root, rb4);
                 GQT_SEL(yb, root, ryb);
-                const unsigned rbk = rb4 < SL_INF ? (((unsigned)(rb4 - ryb) << 10) | 0x300u | (unsigned)root) : 0xffffffffu;
+                const unsigned rbk = rb4 < SL_INF ? (((unsigned)(rb4 - ryb) << TS) | TY3 | (unsigned)root) : 0xffffffffu;
                 const uint32_t ro = (uint32_t)def[root] * N;
                 unsigned best0 = rbk;
                 GQM_STAT(6, 1);
@@ -244,14 +270,14 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                 for (int k = 0; k < K; ++k) {
                     const i32 wt = (i32)dist[ro + dj[k]];      // the diagonal is infinite: the root offers nothing to itself
                     const i32 x = 4 * wt - ryb - yb[k];
-                    ek[k] = wt != (i32)W_INF ? (((unsigned)x << 10) + kb[k]) : EK_NONE;
+                    ek[k] = wt != (i32)W_INF ? (((unsigned)x << TS) + kb[k]) : EK_NONE;
                     best0 = min(best0, ek[k]);
                 }
                 best0 = __reduce_min_sync(GQW_FULL, best0);
-                if (best0 < 0x7ffffc00u) {
-                    const int v0 = best0 & 0xff;
+                if (best0 < EK_LIM) {
+                    const int v0 = best0 & VM;
                     int done = 0;
-                    if (((best0 >> 8) & 3) == 3) {
+                    if (((best0 >> VB) & 3) == 3) {
                         if (lane == 0) f.mate[root] = -2;
                         done = 1;
                     } else if (f.top[v0] == v0 && f.mate[v0] < 0) {
@@ -262,7 +288,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                         GQM_STAT(0, 1); GQM_STAT(4, 1); GQM_STAT(11, 1);
 #pragma unroll
                         for (int k = 0; k < K; ++k)
-                            if (mine && k == rk) yb[k] += (i32)(best0 >> 10);
+                            if (mine && k == rk) yb[k] += (i32)(best0 >> TS);
                         __syncwarp();
                         continue;
                     }
@@ -273,29 +299,29 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     // source in the type bits: 0 root -> k (the offers above), 1 w0 -> k, 2 the edge root - w0 turning
                     // tight (a blossom: left to the tree code), 3 boundary of root / w0.
                     const int w0 = f.top[v0] == v0 ? (int)f.mate[v0] : -1;
-                    if (((best0 >> 8) & 3) == 0 && w0 >= 0 && f.top[w0] == w0) {
-                        const i32 t1 = (i32)(best0 >> 10);
+                    if (((best0 >> VB) & 3) == 0 && w0 >= 0 && f.top[w0] == w0) {
+                        const i32 t1 = (i32)(best0 >> TS);
                         i32 yw, wb4;
                         GQT_SEL(yb, w0, yw);
                         GQT_SEL(b4, w0, wb4);
                         const uint32_t rw = (uint32_t)def[w0] * N;
                         const i32 ew = t1 - yw;          // w0 reaches k at clock 4 d(w0, k) - y_k + ew
                         unsigned b2 = rbk;
-                        if (wb4 < SL_INF) b2 = min(b2, ((unsigned)(wb4 + ew) << 10) | 0x300u | (unsigned)w0);
+                        if (wb4 < SL_INF) b2 = min(b2, ((unsigned)(wb4 + ew) << TS) | TY3 | (unsigned)w0);
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
                             const int x = lane + GQW_LANES * k;
                             const i32 wt = (i32)dist[rw + dj[k]];
                             unsigned c = ek[k];
                             if (x == v0) c = 0xffffffffu;
-                            if (x == w0) c = ek_has(ek[k]) ? (((unsigned)((ek_time(ek[k]) + t1) >> 1) << 10) | 0x200u | (unsigned)x) : 0xffffffffu;
+                            if (x == w0) c = ek_has<TS>(ek[k]) ? (((unsigned)((ek_time<TS>(ek[k]) + t1) >> 1) << TS) | TY2 | (unsigned)x) : 0xffffffffu;
                             const unsigned c2 = (wt != (i32)W_INF && x != v0 && x != root)
-                                                    ? ((((unsigned)(4 * wt - yb[k] + ew)) << 10) | 0x100u | (unsigned)x) : 0xffffffffu;
+                                                    ? ((((unsigned)(4 * wt - yb[k] + ew)) << TS) | TY1 | (unsigned)x) : 0xffffffffu;
                             b2 = min(b2, min(c, c2));
                         }
                         b2 = __reduce_min_sync(GQW_FULL, b2);
-                        const int ty = (b2 >> 8) & 3, k2 = b2 & 0xff;
-                        if (b2 < 0x7ffffc00u && ty != 2 && (ty == 3 || (f.top[k2] == k2 && f.mate[k2] < 0))) {
+                        const int ty = (b2 >> VB) & 3, k2 = b2 & VM;
+                        if (b2 < EK_LIM && ty != 2 && (ty == 3 || (f.top[k2] == k2 && f.mate[k2] < 0))) {
                             GQM_STAT(0, 2); GQM_STAT(2, 1); GQM_STAT(4, 1); GQM_STAT(6, 1); GQM_STAT(12, 1);
                             const bool from_root = ty == 0 || (ty == 3 && k2 == root);
                             if (lane == 0) {
@@ -304,7 +330,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                                 if (ty == 3) f.mate[src] = -2;
                                 else { f.mate[src] = (i16)k2; f.mate[k2] = (i16)src; }
                             }
-                            const i32 t2 = (i32)(b2 >> 10), dt = t2 - t1;
+                            const i32 t2 = (i32)(b2 >> TS), dt = t2 - t1;
 #pragma unroll
                             for (int k = 0; k < K; ++k) {
                                 const int x = lane + GQW_LANES * k;
@@ -351,17 +377,17 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
 #pragma unroll 1
                     for (int i = lane; i < bhi; i += GQW_LANES)
                         if (f.bused[i] && f.par[cap + i] < 0 && f.label[cap + i] == L_T)
-                            best = min(best, ((unsigned)(f.yb[i] >> 1) << 10) | 0x200u | (unsigned)i);
+                            best = min(best, ((unsigned)(f.yb[i] >> 1) << TS) | TY2 | (unsigned)i);
                 }
                 best = __reduce_min_sync(GQW_FULL, best);
                 GQM_STAT(0, 1);
 #ifdef GQ_MT_STATS
                 ++ph_events;
 #endif
-                if (best >= 0x7ffffc00u) { fail = 1; break; }
-                const i32 t = (i32)(best >> 10);
-                const int type = (best >> 8) & 3;
-                const int arg = best & 0xff;
+                if (best >= EK_LIM) { fail = 1; break; }
+                const i32 t = (i32)(best >> TS);
+                const int type = (best >> VB) & 3;
+                const int arg = best & VM;
                 int src = -1;
                 if (type < 2) GQT_SEL(slfrom, arg, src);
 #ifdef GQ_HOST_SIM
@@ -396,11 +422,11 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                         turned[k] = false;
                         if (vtop[k] == tn) {
                             yb[k] += D;
-                            ek[k] = ek_has(ek[k]) ? ((ek[k] - ((unsigned)D << 10)) | EK_FROZEN) : 0xffffffffu;
+                            ek[k] = ek_has<TS>(ek[k]) ? ((ek[k] - ((unsigned)D << TS)) | EK_FROZEN) : 0xffffffffu;
                             kb[k] = (unsigned)(lane + GQW_LANES * k) | EK_FROZEN;
                         } else if (vtop[k] == sn) {
                             yb[k] -= D; turned[k] = true;
-                            if (ek_has(ek[k])) ek[k] = ((unsigned)((ek_time(ek[k]) + D) >> 1) << 10) | 0x100u | (unsigned)(lane + GQW_LANES * k);
+                            if (ek_has<TS>(ek[k])) ek[k] = ((unsigned)((ek_time<TS>(ek[k]) + D) >> 1) << TS) | TY1 | (unsigned)(lane + GQW_LANES * k);
                             GQT_MAKE_OUTER(k);
                         }
                     }
@@ -451,7 +477,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                             if (GQT_IS_INNER(k)) {
                                 turned[k] = true;
                                 yb[k] -= 2 * D;
-                                ek[k] = ek_has(ek[k]) ? (((unsigned)(D + (ek_time(ek[k]) >> 1)) << 10) | 0x100u | (unsigned)x) : EK_NONE;
+                                ek[k] = ek_has<TS>(ek[k]) ? (((unsigned)(D + (ek_time<TS>(ek[k]) >> 1)) << TS) | TY1 | (unsigned)x) : EK_NONE;
                                 GQT_MAKE_OUTER(k);
                             }
                             vtop[k] = b;
@@ -464,7 +490,7 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     // stale entry can ever win the search
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        if (vtop[k] == b && slfrom[k] >= 0 && ek_has(ek[k]) && f.top[slfrom[k]] == b) {
+                        if (vtop[k] == b && slfrom[k] >= 0 && ek_has<TS>(ek[k]) && f.top[slfrom[k]] == b) {
                             ek[k] = EK_NONE; slfrom[k] = -1; turned[k] = true;
                         }
                         nm[k] = __ballot_sync(GQW_FULL, turned[k]);
@@ -507,11 +533,11 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                             const int nl = f.label[vtop[k]];
                             if (nl == L_S) {
                                 turned = true; yb[k] -= 2 * D;
-                                ek[k] = ek_has(ek[k]) ? (((unsigned)(D + (ek_time(ek[k]) >> 1)) << 10) | 0x100u | (unsigned)x) : EK_NONE;
+                                ek[k] = ek_has<TS>(ek[k]) ? (((unsigned)(D + (ek_time<TS>(ek[k]) >> 1)) << TS) | TY1 | (unsigned)x) : EK_NONE;
                                 GQT_MAKE_OUTER(k);
                             } else if (nl == L_NONE) {
                                 yb[k] -= D;
-                                ek[k] = ek_has(ek[k]) ? (((unsigned)(D + ek_time(ek[k])) << 10) | (unsigned)x) : EK_NONE;
+                                ek[k] = ek_has<TS>(ek[k]) ? (((unsigned)(D + ek_time<TS>(ek[k])) << TS) | (unsigned)x) : EK_NONE;
                                 kb[k] = (unsigned)x;
                             }
                         }
@@ -562,10 +588,12 @@ __device__ __forceinline__ void dual_start(const Tables &T, i16 *xch, const u16 
     const u16 *__restrict__ dist = T.dist;
     const uint32_t N = T.N;
     const uint32_t bro = T.D * N;
+    constexpr int VB = KeyBits<K>::VB;
+    constexpr unsigned VM = KeyBits<K>::VM;
     uint32_t dj[K];
     unsigned key[K];
     bool miss[K];
-    // ---- nearest other defect of every defect: key = distance << 8 | index.
+    // ---- nearest other defect of every defect: key = distance << VB | index.
     // Lane-parallel: test the NBR_LEN nearest detectors of each own defect against the syndrome bits
     // (descending, so the nearest hit is the one that sticks); any hit is the true nearest defect because
     // the list is a complete prefix of the detector's distance order.
@@ -595,7 +623,7 @@ __device__ __forceinline__ void dual_start(const Tables &T, i16 *xch, const u16 
             if (hit != 0xffffffffu) {
                 const uint32_t det = hit & 0xffffu;
                 const uint32_t rank = (uint32_t)spre[det >> 5] + (uint32_t)__popc(synw[det >> 5] & ((1u << (det & 31)) - 1u));
-                key[k] = ((hit >> 16) << 8) | rank;
+                key[k] = ((hit >> 16) << VB) | rank;
                 miss[k] = false;
             }
         }
@@ -618,7 +646,7 @@ __device__ __forceinline__ void dual_start(const Tables &T, i16 *xch, const u16 
                     const uint32_t ro = (uint32_t)def[i] * N;
                     unsigned best = 0xffffffffu;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) best = min(best, (unsigned)dist[ro + dj[k]] * 256u + (unsigned)(lane + GQW_LANES * k));
+                    for (int k = 0; k < K; ++k) best = min(best, ((unsigned)dist[ro + dj[k]] << VB) + (unsigned)(lane + GQW_LANES * k));
                     best = __reduce_min_sync(GQW_FULL, best);
 #pragma unroll
                     for (int k = 0; k < K; ++k) if (lane + GQW_LANES * k == i) key[k] = best;
@@ -633,11 +661,11 @@ __device__ __forceinline__ void dual_start(const Tables &T, i16 *xch, const u16 
         const int v = lane + GQW_LANES * k;
         const uint32_t bb = dist[bro + dj[k]];
         const i32 b4 = bb == (uint32_t)W_INF ? SL_INF : 4 * (i32)bb;
-        const uint32_t wmin = key[k] >> 8;
+        const uint32_t wmin = key[k] >> VB;
         const i32 y2 = wmin >= (uint32_t)W_INF ? SL_INF : 2 * (i32)wmin;
         onb[k] = b4 < SL_INF && b4 <= y2;
         yb[k] = onb[k] ? b4 : (y2 < SL_INF ? y2 : 0);
-        if (v < n) xch[v] = (i16)((onb[k] || y2 == SL_INF) ? -1 : (int)(key[k] & 0xff));
+        if (v < n) xch[v] = (i16)((onb[k] || y2 == SL_INF) ? -1 : (int)(key[k] & VM));
     }
     __syncwarp();
 #pragma unroll

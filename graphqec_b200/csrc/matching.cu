@@ -328,8 +328,15 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
 #define GQ_SIDE_STREAMS 0   // 1: the smaller classes' kernels run on side streams (overlapping tails, but co-resident
                             // kernels share the instruction cache: measured slower once start/solve were split)
 #endif
-static constexpr int MT_CLASSES = 8;     // K = 1 .. 8 (the event keys hold the vertex in 8 bits: 256 defects is the limit)
-static constexpr int MT_CAP = 32 * MT_CLASSES;
+// classes 0..7: K = 1..8 (8-bit vertex field, up to 256 defects); classes 8..10: K = 10, 12, 16 (9-bit field, up to 512)
+static constexpr int MT_CLASSES = 11;
+static constexpr int MT_CAP = 512;
+__host__ __device__ constexpr int mt_class_of(int n) {   // n >= 1 defects -> class, MT_CLASSES = beyond the first tier
+    return n <= 256 ? (n - 1) >> 5 : (n <= 320 ? 8 : (n <= 384 ? 9 : (n <= 512 ? 10 : MT_CLASSES)));
+}
+template <int K> struct MtClassRange {     // defect counts a class-K list may hold: (LO, 32 K]
+    static constexpr int LO = K <= 8 ? 32 * (K - 1) : (K == 10 ? 256 : (K == 12 ? 320 : 384));
+};
 
 template <int K>
 struct MtWarpMem {
@@ -365,7 +372,7 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyArgs a) {
             if (a.D & 31) last &= (1u << (a.D & 31)) - 1;
             n += __popc(last);
         }
-        const int cls = n < 0 ? -1 : (n == 0 ? -2 : (n > MT_CAP ? MT_CLASSES : (n - 1) >> 5));
+        const int cls = n < 0 ? -1 : (n == 0 ? -2 : mt_class_of(n));
         if (cls == -2) {
             for (uint32_t w = 0; w < a.OW; ++w) a.pred[(size_t)shot * a.OW + w] = 0u;
             if (a.weight_out) a.weight_out[shot] = 0;
@@ -409,7 +416,7 @@ struct StartWarpMem {
 };
 
 template <int K>
-__global__ void __launch_bounds__(256, (K <= 4 ? 8 : (K <= 6 ? 4 : 3))) tree_start_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(256, (K <= 4 ? 8 : (K <= 6 ? 4 : (K <= 8 ? 3 : 1)))) tree_start_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(256, (K <= 4 ? 8 : (K <= 6 ? 4 : 3))) tree_sta
         const int n0 = gqt::extract_defects(a.dets + (size_t)shot * a.DW, a.DW, a.D, lane, M.def, 32 * K,
                                             mirror ? M.synw : nullptr, M.spre);
         StartRecord<K> &R = recs[item];
-        if (n0 > 32 * K || n0 <= 32 * (K - 1)) {   // the list lied about the defect count: the solver will hand it on
+        if (n0 > 32 * K || n0 <= MtClassRange<K>::LO) {   // the list lied about the defect count: the solver will hand it on
             if (lane == 0) R.n = 0xffffffffu;
             __syncwarp();
             continue;
@@ -537,7 +544,10 @@ static size_t start_record_bytes(int c) {   // class c = K - 1
     case 4: return sizeof(StartRecord<5>);
     case 5: return sizeof(StartRecord<6>);
     case 6: return sizeof(StartRecord<7>);
-    default: return sizeof(StartRecord<8>);
+    case 7: return sizeof(StartRecord<8>);
+    case 8: return sizeof(StartRecord<10>);
+    case 9: return sizeof(StartRecord<12>);
+    default: return sizeof(StartRecord<16>);
     }
 }
 
@@ -746,7 +756,8 @@ int gq_matching_create(gq_dec *dec) {
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     if (configure_tree_class<1>() || configure_tree_class<2>() || configure_tree_class<3>() || configure_tree_class<4>() ||
-        configure_tree_class<5>() || configure_tree_class<6>() || configure_tree_class<7>() || configure_tree_class<8>())
+        configure_tree_class<5>() || configure_tree_class<6>() || configure_tree_class<7>() || configure_tree_class<8>() ||
+        configure_tree_class<10>() || configure_tree_class<12>() || configure_tree_class<16>())
         GQ_FAIL(GQ_E_CUDA, "matching decoder: cudaFuncSetAttribute failed for the first-tier kernels");
     GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << GQ_SLICE_LOG2) + 16) * 4));
     for (int i = 0; i < MT_CLASSES - 1; ++i) {
@@ -857,7 +868,10 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
                 case 4: lrc = launch_tree_class<5>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 case 5: lrc = launch_tree_class<6>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 case 6: lrc = launch_tree_class<7>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                default: lrc = launch_tree_class<8>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 7: lrc = launch_tree_class<8>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 8: lrc = launch_tree_class<10>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 9: lrc = launch_tree_class<12>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                default: lrc = launch_tree_class<16>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 }
                 if (lrc) GQ_FAIL(lrc, "matching decoder: first-tier kernel launch failed");
                 if (st != dem->stream) {
@@ -871,7 +885,7 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
             if (counts[dom]) {
                 float ms = 0;
                 cudaEventElapsedTime(&ms, dec->kev0, dec->kev1);
-                dec->kprof[0] += ms; dec->kprof[1] += 1; dec->kprof[2] += counts[dom]; dec->kprof[3] = dom + 1;
+                dec->kprof[0] += ms; dec->kprof[1] += 1; dec->kprof[2] += counts[dom]; dec->kprof[3] = dom < 8 ? dom + 1 : (dom == 8 ? 10 : (dom == 9 ? 12 : 16));
             }
             if (ovf[0] == 0) continue;
             if (ovf[0] > dec->overflow_cap) GQ_FAIL(GQ_E_INTERNAL, "matching decoder: overflow list overrun");

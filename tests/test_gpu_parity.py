@@ -283,14 +283,16 @@ def test_decode_b8_growing_chunk_schedule_equals_device_path():
 
 
 def test_every_first_tier_class_and_the_ladder_give_the_optimum():
-    """syndromes with 1 .. 300 defects: classes K = 1..8 of the first tier, then the older tiers"""
+    """syndromes with 1 .. 700 defects: classes K = 1..8 (8-bit vertex keys) and K = 10, 12, 16 (9-bit keys) of the
+    first tier, then the older tiers"""
     import torch
-    dem, demh, dech = case("rot7")
+    dem, demh, dech = case("rot11")
     rng = np.random.default_rng(3)
     D = dem.num_detectors
-    counts = [1, 2, 31, 32, 33, 64, 65, 96, 97, 128, 129, 160, 161, 192, 193, 224, 225, 255, 256, 257, 300]
-    rows = np.zeros((len(counts) * 3, demh.DW), dtype=np.uint32)
-    for i, c in enumerate(counts * 3):
+    counts = [1, 2, 31, 32, 33, 64, 65, 96, 97, 128, 129, 160, 161, 192, 193, 224, 225, 255, 256, 257, 300, 320, 321,
+              384, 385, 450, 512, 513, 700]
+    rows = np.zeros((len(counts) * 2, demh.DW), dtype=np.uint32)
+    for i, c in enumerate(counts * 2):
         for k in rng.choice(D, size=min(c, D), replace=False):
             rows[i, k >> 5] |= np.uint32(1) << np.uint32(k & 31)
     t = torch.from_numpy(rows.view(np.int32)).cuda()

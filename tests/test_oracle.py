@@ -151,17 +151,21 @@ def test_decoder_matching_core_handles_missing_edges(hostsim):
 # first tier of the CUDA matching decoder (match_tree.cuh) compiled for the host with one lane
 # ------------------------------------------------------------------------------------------
 
-@pytest.fixture(scope="module")
-def tree_hostsim():
-    so = os.path.join(ROOT, "tests", "hostsim", "libmthostsim.so")
+@pytest.fixture(scope="module", params=[128, 512], ids=["cap128_8bit_keys", "cap512_9bit_keys"])
+def tree_hostsim(request):
+    """one-lane host build of match_tree.cuh; capacity 128 uses the 8-bit vertex field of the K <= 8 kernels,
+    capacity 512 the 9-bit field of the K = 10, 12, 16 kernels"""
+    cap = request.param
+    so = os.path.join(ROOT, "tests", "hostsim", f"libmthostsim_{cap}.so")
     srcs = [os.path.join(ROOT, "tests", "hostsim", f) for f in ("mt_hostsim.cpp", "warp_sim.h")]
     srcs += [os.path.join(ROOT, "graphqec_b200", "csrc", f) for f in ("match_tree.cuh", "blossom_regs.cuh")]
     if not os.path.exists(so) or max(os.path.getmtime(s) for s in srcs) > os.path.getmtime(so):
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", f"-DHS_CAP={cap}", "-o", so, srcs[0]])
     lib = ctypes.CDLL(so)
     lib.hostsim_mt_decode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_long] + [ctypes.c_void_p] * 5
     lib.hostsim_mt_stats.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.cap = cap
     return lib
 
 
@@ -243,6 +247,23 @@ def test_tree_tier_is_exact_on_random_graphs_with_blossoms(tree_hostsim):
         assert (rc == 0).all() and (wt == owt).all(), (trial, np.where(wt != owt)[0][:5])
     tree_hostsim.hostsim_mt_stats(stats, 0)
     assert stats[3] > 200 and stats[7] > 5    # shrinks and expands were exercised
+
+
+def test_tree_tier_is_exact_on_dense_syndromes(tree_hostsim):
+    """rotated d = 11 at p = 1.5 %: ~230 defects per shot; shots beyond the build's capacity report code 4"""
+    code = RotatedSurfaceCode(distance=11, depolarize1_rate=0.015, depolarize2_rate=0.015)
+    code.build_memory_circuit(number_of_rounds=11, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model(decompose_errors=True)
+    orc = po.MwpmOracle(dem)
+    dets, _ = po.sample(dem, 11, 200)
+    nd = np.unpackbits(dets, axis=1, bitorder="little")[:, :dem.num_detectors].sum(1)
+    opred, owt = orc.decode_batch(dets, return_weights=True)
+    pred, wt, rc = _tree_decode(tree_hostsim, orc, dets)
+    fits = nd <= tree_hostsim.cap
+    assert (rc[fits] == 0).all() and (rc[~fits] == 4).all()
+    assert (wt[fits] == owt[fits]).all()
+    if tree_hostsim.cap == 512:
+        assert fits.all() and (nd > 128).sum() > 100
 
 
 def test_tree_tier_reports_undecodable_syndromes(tree_hostsim):
