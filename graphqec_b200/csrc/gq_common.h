@@ -69,8 +69,8 @@ struct gq_dec {
     double timing[8] = {0};
     double kprof[4] = {0};             // dominant first-tier kernel of the last call: {ms, launches, shots, K}
     cudaEvent_t kev0 = nullptr, kev1 = nullptr;
-    cudaStream_t side_streams[10] = {};   // first tier: the smaller classes' kernels
-    cudaEvent_t side_done[10] = {};
+    cudaStream_t side_streams[12] = {};   // first tier: the smaller classes' kernels
+    cudaEvent_t side_done[12] = {};
     // ---- matching
     uint32_t num_edges = 0, num_boundary = 0;
     std::vector<uint32_t> eu, ev, ew;

@@ -114,6 +114,13 @@ __device__ __forceinline__ int extract_defects(const uint32_t *row, uint32_t DW,
 
 // arr[slot] for a warp-uniform slot, written as a select tree on the bits of slot: a chain of
 // "slot == k" selects gets folded back into a dynamically indexed (local-memory) array by the compiler
+// generic select tree over [LO, LO + N), N a power of two; indices at or beyond K read as 0
+template <int LO, int N, int K, class TV>
+__device__ __forceinline__ int sel_rec(const TV (&arr)[K], const int slot) {
+    if constexpr (N == 1) return LO < K ? (int)arr[LO < K ? LO : 0] : 0;
+    else return (slot & (N / 2)) ? sel_rec<LO + N / 2, N / 2, K>(arr, slot) : sel_rec<LO, N / 2, K>(arr, slot);
+}
+
 template <int K, class TV>
 __device__ __forceinline__ int sel_slot(const TV (&arr)[K], const int slot) {
     if constexpr (K == 1) return (int)arr[0];
@@ -147,6 +154,8 @@ __device__ __forceinline__ int sel_slot(const TV (&arr)[K], const int slot) {
             hi = (slot & 4) ? b1 : b0;
         }
         return (slot & 8) ? hi : lo;
+    } else if constexpr (K <= 32) {
+        return sel_rec<0, 32, K>(arr, slot);
     } else return (int)arr[slot];
 }
 
@@ -164,13 +173,13 @@ __device__ __forceinline__ int sel_slot(const TV (&arr)[K], const int slot) {
 // Label of a slot = the key bits it contributes: kb = vertex (unlabelled), vertex | 0x100 (outer),
 // vertex | bit 31 (inner).  With X = 4w - y_u + (D - yb[k]) the candidate time of an edge from outer u
 // is X for unlabelled and inner targets (time resp. frozen slack) and X / 2 for outer ones.
-// Field widths: the vertex takes VB = 8 bits up to 256 defects per shot and 9 bits beyond (up to 512), the
-// type 2 bits above it, the time the rest below bit 31 (21 resp. 20 bits; times stay below 2^20: they are
+// Field widths: the vertex takes VB = 8 bits up to 256 defects per shot, 9 bits up to 512 and 10 bits up to 1024,
+// the type 2 bits above it, the time the rest below bit 31 (21, 20 resp. 19 bits; times stay below 2^19: they are
 // bounded by 8 x the largest table distance, a u16).
 static const unsigned EK_NONE = 0x7fffffffu;   // no pending edge event (time field all ones)
 static const unsigned EK_FROZEN = 0x80000000u;
 template <int K> struct KeyBits {
-    static constexpr int VB = (K * GQW_LANES > 256) ? 9 : 8;
+    static constexpr int VB = (K * GQW_LANES > 512) ? 10 : ((K * GQW_LANES > 256) ? 9 : 8);
     static constexpr int TS = VB + 2;
     static constexpr unsigned VM = (1u << VB) - 1u;
     static constexpr unsigned TY1 = 1u << VB, TY2 = 2u << VB, TY3 = 3u << VB;

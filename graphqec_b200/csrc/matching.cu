@@ -328,14 +328,17 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
 #define GQ_SIDE_STREAMS 0   // 1: the smaller classes' kernels run on side streams (overlapping tails, but co-resident
                             // kernels share the instruction cache: measured slower once start/solve were split)
 #endif
-// classes 0..7: K = 1..8 (8-bit vertex field, up to 256 defects); classes 8..10: K = 10, 12, 16 (9-bit field, up to 512)
-static constexpr int MT_CLASSES = 11;
-static constexpr int MT_CAP = 512;
+// classes 0..7: K = 1..8 (8-bit vertex field, up to 256 defects); 8..10: K = 10, 12, 16 (9-bit field, up to 512);
+// 11, 12: K = 24, 32 (10-bit field, up to 1024; part of the per-lane state lives in local memory there)
+static constexpr int MT_CLASSES = 13;
+static constexpr int MT_CAP = 1024;
 __host__ __device__ constexpr int mt_class_of(int n) {   // n >= 1 defects -> class, MT_CLASSES = beyond the first tier
-    return n <= 256 ? (n - 1) >> 5 : (n <= 320 ? 8 : (n <= 384 ? 9 : (n <= 512 ? 10 : MT_CLASSES)));
+    return n <= 256 ? (n - 1) >> 5
+                    : (n <= 320 ? 8 : (n <= 384 ? 9 : (n <= 512 ? 10 : (n <= 768 ? 11 : (n <= 1024 ? 12 : MT_CLASSES)))));
 }
 template <int K> struct MtClassRange {     // defect counts a class-K list may hold: (LO, 32 K]
-    static constexpr int LO = K <= 8 ? 32 * (K - 1) : (K == 10 ? 256 : (K == 12 ? 320 : 384));
+    static constexpr int LO = K <= 8 ? 32 * (K - 1) : (K == 10 ? 256 : (K == 12 ? 320 : (K == 16 ? 384 : (K == 24 ? 512 : 768))));
+    static constexpr int WPB = K <= 16 ? 8 : 4;   // warps per block: the K = 24, 32 forests are 30 .. 41 KB per warp
 };
 
 template <int K>
@@ -416,7 +419,7 @@ struct StartWarpMem {
 };
 
 template <int K>
-__global__ void __launch_bounds__(256, (K <= 4 ? 8 : (K <= 6 ? 4 : (K <= 8 ? 3 : 1)))) tree_start_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 4 ? 8 : (K <= 6 ? 4 : (K <= 8 ? 3 : 1)))) tree_start_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(256, (K <= 4 ? 8 : (K <= 6 ? 4 : (K <= 8 ? 3 :
 // throughput instantiation leaves that code out, which is worth it because the kernel is at the edge of
 // the instruction cache
 template <int K, bool EXTRAS>
-__global__ void __launch_bounds__(256, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? 2 : 1)))) tree_solve_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? 2 : 1)))) tree_solve_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -513,14 +516,15 @@ __global__ void __launch_bounds__(256, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_
 
 template <int K>
 static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, int *launches, cudaEvent_t ev0, cudaEvent_t ev1) {
-    const int blocks_a = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * 8);   // latency-bound: all 64 warps/SM
-    tree_start_kernel<K><<<blocks_a, 256, 8 * sizeof(StartWarpMem<K>), st>>>(b);
+    constexpr int WPB = MtClassRange<K>::WPB;
+    const int blocks_a = (int)std::min<uint64_t>((b.nitems + WPB - 1) / WPB, (uint64_t)dem->num_sms * 8);   // latency-bound: all 64 warps/SM
+    tree_start_kernel<K><<<blocks_a, 32 * WPB, WPB * sizeof(StartWarpMem<K>), st>>>(b);
     if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
     const int per_sm = K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? 2 : 1));
-    const int blocks_b = (int)std::min<uint64_t>((b.nitems + 7) / 8, (uint64_t)dem->num_sms * per_sm);
+    const int blocks_b = (int)std::min<uint64_t>((b.nitems + WPB - 1) / WPB, (uint64_t)dem->num_sms * per_sm);
     if (ev0) cudaEventRecord(ev0, st);   // bench.py's roofline times the solve kernel of the biggest class
-    if (b.weight_out || b.flags_out || b.corr_out) tree_solve_kernel<K, true><<<blocks_b, 256, 8 * sizeof(MtWarpMem<K>), st>>>(b);
-    else tree_solve_kernel<K, false><<<blocks_b, 256, 8 * sizeof(MtWarpMem<K>), st>>>(b);
+    if (b.weight_out || b.flags_out || b.corr_out) tree_solve_kernel<K, true><<<blocks_b, 32 * WPB, WPB * sizeof(MtWarpMem<K>), st>>>(b);
+    else tree_solve_kernel<K, false><<<blocks_b, 32 * WPB, WPB * sizeof(MtWarpMem<K>), st>>>(b);
     if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
     if (ev1) cudaEventRecord(ev1, st);
     *launches += 2;
@@ -529,9 +533,9 @@ static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, i
 
 template <int K>
 static int configure_tree_class() {
-    if (cudaFuncSetAttribute(tree_start_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(StartWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
-    if (cudaFuncSetAttribute(tree_solve_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
-    if (cudaFuncSetAttribute(tree_solve_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(MtWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
+    if (cudaFuncSetAttribute(tree_start_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MtClassRange<K>::WPB * sizeof(StartWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
+    if (cudaFuncSetAttribute(tree_solve_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MtClassRange<K>::WPB * sizeof(MtWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
+    if (cudaFuncSetAttribute(tree_solve_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MtClassRange<K>::WPB * sizeof(MtWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
     return GQ_OK;
 }
 
@@ -547,7 +551,9 @@ static size_t start_record_bytes(int c) {   // class c = K - 1
     case 7: return sizeof(StartRecord<8>);
     case 8: return sizeof(StartRecord<10>);
     case 9: return sizeof(StartRecord<12>);
-    default: return sizeof(StartRecord<16>);
+    case 10: return sizeof(StartRecord<16>);
+    case 11: return sizeof(StartRecord<24>);
+    default: return sizeof(StartRecord<32>);
     }
 }
 
@@ -757,7 +763,8 @@ int gq_matching_create(gq_dec *dec) {
     GQ_CUDA(cudaFuncSetAttribute(match_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     if (configure_tree_class<1>() || configure_tree_class<2>() || configure_tree_class<3>() || configure_tree_class<4>() ||
         configure_tree_class<5>() || configure_tree_class<6>() || configure_tree_class<7>() || configure_tree_class<8>() ||
-        configure_tree_class<10>() || configure_tree_class<12>() || configure_tree_class<16>())
+        configure_tree_class<10>() || configure_tree_class<12>() || configure_tree_class<16>() ||
+        configure_tree_class<24>() || configure_tree_class<32>())
         GQ_FAIL(GQ_E_CUDA, "matching decoder: cudaFuncSetAttribute failed for the first-tier kernels");
     GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << GQ_SLICE_LOG2) + 16) * 4));
     for (int i = 0; i < MT_CLASSES - 1; ++i) {
@@ -871,7 +878,9 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
                 case 7: lrc = launch_tree_class<8>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 case 8: lrc = launch_tree_class<10>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 case 9: lrc = launch_tree_class<12>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                default: lrc = launch_tree_class<16>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 10: lrc = launch_tree_class<16>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 11: lrc = launch_tree_class<24>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                default: lrc = launch_tree_class<32>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 }
                 if (lrc) GQ_FAIL(lrc, "matching decoder: first-tier kernel launch failed");
                 if (st != dem->stream) {
@@ -885,7 +894,7 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
             if (counts[dom]) {
                 float ms = 0;
                 cudaEventElapsedTime(&ms, dec->kev0, dec->kev1);
-                dec->kprof[0] += ms; dec->kprof[1] += 1; dec->kprof[2] += counts[dom]; dec->kprof[3] = dom < 8 ? dom + 1 : (dom == 8 ? 10 : (dom == 9 ? 12 : 16));
+                dec->kprof[0] += ms; dec->kprof[1] += 1; dec->kprof[2] += counts[dom]; dec->kprof[3] = dom < 8 ? dom + 1 : (dom == 8 ? 10 : (dom == 9 ? 12 : (dom == 10 ? 16 : (dom == 11 ? 24 : 32))));
             }
             if (ovf[0] == 0) continue;
             if (ovf[0] > dec->overflow_cap) GQ_FAIL(GQ_E_INTERNAL, "matching decoder: overflow list overrun");

@@ -283,14 +283,14 @@ def test_decode_b8_growing_chunk_schedule_equals_device_path():
 
 
 def test_every_first_tier_class_and_the_ladder_give_the_optimum():
-    """syndromes with 1 .. 700 defects: classes K = 1..8 (8-bit vertex keys) and K = 10, 12, 16 (9-bit keys) of the
-    first tier, then the older tiers"""
+    """syndromes with 1 .. 1200 defects: classes K = 1..8 (8-bit vertex keys), K = 10, 12, 16 (9-bit keys) and
+    K = 24, 32 (10-bit keys) of the first tier, then the older tier"""
     import torch
     dem, demh, dech = case("rot11")
     rng = np.random.default_rng(3)
     D = dem.num_detectors
     counts = [1, 2, 31, 32, 33, 64, 65, 96, 97, 128, 129, 160, 161, 192, 193, 224, 225, 255, 256, 257, 300, 320, 321,
-              384, 385, 450, 512, 513, 700]
+              384, 385, 450, 512, 513, 700, 768, 769, 1000, 1024, 1025, 1200]
     rows = np.zeros((len(counts) * 2, demh.DW), dtype=np.uint32)
     for i, c in enumerate(counts * 2):
         for k in rng.choice(D, size=min(c, D), replace=False):
