@@ -12,6 +12,17 @@
 // sign parity are combined with warp shuffles, and the same sweep evaluates the parity of the
 // current hard decision, so convergence (H.e == s) costs no extra pass.
 // Summation order and tie rules equal oracle/bp_oracle.c, so results match it bit for bit.
+//
+// OSD-0 (params.bp_osd; the "OSD" of the reference's decoder="bposd") for the shots BP
+// leaves unconverged, in two steps:
+//  * bp_kernel's epilogue picks the osd_k variables with the smallest posterior LLR, in order (ties by
+//    index): 4-pass radix select of the k-th key over the block's posterior array, index-ordered
+//    compaction of everything below it, bitonic sort of the k (key, index) pairs in shared memory;
+//  * osd_solve_kernel, one warp per shot, walks those candidates: a column of H joins the basis iff it is
+//    independent of the columns already in it (incremental GF(2) elimination on D-bit vectors spread over
+//    the lanes, pivot = lowest set bit, found with a ballot), and the walk stops the moment the syndrome
+//    reduces to zero against the basis -- its representation in a basis is unique, so the later basis
+//    columns of a full OSD-0 would get coefficient 0.  Identical to oracle/bp_oracle.c::orc_osd0.
 #include <math.h>
 #include <string.h>
 
@@ -35,7 +46,84 @@ struct BpArgs {
     int max_iter;
     float alpha;
     int use_shared;
+    // OSD-0 hand-off (osd_k = 0: off)
+    uint32_t osd_k;
+    uint32_t *cand;          // [capacity][osd_k] candidate variables of every unconverged shot, most likely first
+    uint32_t *fail_list;     // [capacity] the unconverged shots
+    uint32_t *fail_count;
 };
+
+
+static constexpr int OSD_KMAX = 1024;     // candidates kept per shot (and the cap on the basis size)
+
+__device__ __forceinline__ uint32_t osd_key(float x) {   // order-preserving map float -> uint32
+    const uint32_t b = __float_as_uint(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// The k variables with the smallest posterior, ascending (ties by index), written to out[0..k); k <= OSD_KMAX.
+// All 256 threads of the block call it; tot[] holds the block's M posteriors.
+__device__ void osd_select(const float *tot, uint32_t M, uint32_t k, uint32_t *out) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_rank;
+    __shared__ uint32_t cnt_less[256], cnt_tie[256];
+    __shared__ unsigned long long pairs[OSD_KMAX];
+    __shared__ uint32_t s_fill;
+    const int tid = threadIdx.x;
+    if (k > M) k = M;
+    // ---- k-th smallest key by 8-bit digits, most significant first
+    uint32_t prefix = 0, mask = 0, rank = k;        // rank: 1-based rank still to find inside the prefix group
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        for (uint32_t v = tid; v < M; v += 256) {
+            const uint32_t key = osd_key(tot[v]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t cum = 0, d = 0;
+            for (; d < 256; ++d) { if (cum + hist[d] >= rank) break; cum += hist[d]; }
+            s_prefix = prefix | (d << shift);
+            s_rank = rank - cum;
+        }
+        __syncthreads();
+        prefix = s_prefix; rank = s_rank; mask |= 255u << shift;
+        __syncthreads();
+    }
+    const uint32_t kth = prefix, need_ties = rank;   // keys < kth all belong; of the keys == kth the first need_ties by index
+    // ---- index-ordered compaction: thread t owns the contiguous chunk [t * C, (t + 1) * C)
+    const uint32_t C = (M + 255) / 256, lo = tid * C, hi = min(M, lo + C);
+    uint32_t nl = 0, nt = 0;
+    for (uint32_t v = lo; v < hi; ++v) { const uint32_t key = osd_key(tot[v]); nl += key < kth; nt += key == kth; }
+    cnt_less[tid] = nl; cnt_tie[tid] = nt;
+    if (tid == 0) s_fill = 0;
+    for (uint32_t i = tid; i < OSD_KMAX; i += 256) pairs[i] = ~0ull;
+    __syncthreads();
+    uint32_t tie_before = 0;
+    for (int t = 0; t < tid; ++t) tie_before += cnt_tie[t];
+    for (uint32_t v = lo; v < hi; ++v) {
+        const uint32_t key = osd_key(tot[v]);
+        bool take = key < kth;
+        if (key == kth) { take = tie_before < need_ties; ++tie_before; }
+        if (take) pairs[atomicAdd(&s_fill, 1u)] = ((unsigned long long)key << 32) | v;
+    }
+    __syncthreads();
+    // ---- bitonic sort of the (key, index) pairs (padding sorts last)
+    for (uint32_t size = 2; size <= OSD_KMAX; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = tid; i < OSD_KMAX / 2; i += 256) {
+                const uint32_t a = 2 * i - (i & (stride - 1)), b = a + stride;
+                const bool up = (a & size) == 0;
+                const unsigned long long x = pairs[a], y = pairs[b];
+                if ((x > y) == up) { pairs[a] = y; pairs[b] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = tid; i < OSD_KMAX; i += 256) out[i] = i < k ? (uint32_t)pairs[i] : 0xFFFFFFFFu;
+    __syncthreads();
+}
 
 __global__ void __launch_bounds__(256) bp_kernel(BpArgs a) {
     extern __shared__ float smem[];
@@ -122,8 +210,142 @@ __global__ void __launch_bounds__(256) bp_kernel(BpArgs a) {
             if (a.flags_out) a.flags_out[shot] = converged ? 0 : 1;
         }
         __syncthreads();
+        if (a.osd_k && !converged) {
+            // hand the shot to OSD-0: its osd_k most likely error mechanisms, in order
+            __shared__ uint32_t s_slot;
+            if (tid == 0) { s_slot = atomicAdd(a.fail_count, 1u); a.fail_list[s_slot] = (uint32_t)shot; }
+            __syncthreads();
+            osd_select(tot, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_KMAX);
+        }
     }
 }
+
+
+// ---- OSD-0 walk, one warp per unconverged shot.  A D-bit vector is spread over the lanes: word w lives in
+// slot w / 32 of lane w % 32, so the lowest set bit is one ballot per slot.  Basis vectors and their
+// coefficient sets (one bit per basis ordinal, 32 ordinals per lane) live in a per-warp HBM/L2 scratch; every
+// lane only ever reads back the words it wrote itself.
+struct OsdArgs {
+    const uint32_t *dets;
+    uint32_t *pred;
+    uint8_t *flags_out;
+    uint32_t *corr_out;
+    const uint32_t *cand, *fail_list;
+    uint32_t nfail;
+    uint32_t D, DW, OW, MW, M;
+    const uint32_t *var_ptr, *var_chk, *var_obs;
+    uint32_t *scratch;        // per warp: OSD_KMAX x (32 WPL basis words + 32 coefficient words) + OSD_KMAX columns
+    size_t scratch_stride;    // words
+};
+
+template <int WPL>
+__device__ __forceinline__ int osd_lowbit(const uint32_t (&v)[WPL], int lane) {
+#pragma unroll
+    for (int j = 0; j < WPL; ++j) {
+        const unsigned m = __ballot_sync(0xffffffffu, v[j] != 0u);
+        if (m) {
+            const int l = __ffs(m) - 1;
+            const uint32_t w = __shfl_sync(0xffffffffu, v[j], l);
+            return ((j * 32 + l) << 5) + __ffs(w) - 1;
+        }
+    }
+    return -1;
+}
+
+template <int WPL>
+__global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
+    extern __shared__ uint16_t piv_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint16_t *piv = piv_all + (size_t)wib * ((a.D + 1) & ~1u);
+    uint32_t *basis = a.scratch + (size_t)warp * a.scratch_stride;
+    uint32_t *coef = basis + (size_t)OSD_KMAX * 32 * WPL;
+    uint32_t *col = coef + (size_t)OSD_KMAX * 32;
+    for (uint32_t item = warp; item < a.nfail; item += nwarps) {
+        const uint32_t shot = a.fail_list[item];
+        const uint32_t *cand = a.cand + (size_t)item * OSD_KMAX;
+        for (uint32_t r = lane; r < a.D; r += 32) piv[r] = 0xFFFFu;
+        uint32_t s[WPL], sc = 0;
+#pragma unroll
+        for (int j = 0; j < WPL; ++j) {
+            const uint32_t w = j * 32 + lane;
+            uint32_t word = w < a.DW ? a.dets[(size_t)shot * a.DW + w] : 0u;
+            if (w == a.DW - 1 && (a.D & 31)) word &= (1u << (a.D & 31)) - 1u;
+            s[j] = word;
+        }
+        __syncwarp();
+        int nb = 0;
+        bool done = false;
+        // reduce the syndrome against the basis; done when nothing is left of it
+        auto reduce_s = [&]() {
+            for (;;) {
+                const int r = osd_lowbit<WPL>(s, lane);
+                if (r < 0) { done = true; return; }
+                const uint32_t p = piv[r];
+                if (p == 0xFFFFu) return;
+#pragma unroll
+                for (int j = 0; j < WPL; ++j) s[j] ^= basis[((size_t)p * WPL + j) * 32 + lane];
+                sc ^= coef[(size_t)p * 32 + lane];
+            }
+        };
+        reduce_s();
+        for (uint32_t i = 0; i < OSD_KMAX && !done && nb < OSD_KMAX; ++i) {
+            const uint32_t c = cand[i];
+            if (c == 0xFFFFFFFFu) break;
+            uint32_t v[WPL], vc = 0;
+#pragma unroll
+            for (int j = 0; j < WPL; ++j) v[j] = 0u;
+            for (uint32_t k = a.var_ptr[c]; k < a.var_ptr[c + 1]; ++k) {
+                const uint32_t d = a.var_chk[k], w = d >> 5;
+#pragma unroll
+                for (int j = 0; j < WPL; ++j)
+                    if ((int)(w >> 5) == j && (int)(w & 31u) == lane) v[j] ^= 1u << (d & 31u);
+            }
+            for (;;) {
+                const int r = osd_lowbit<WPL>(v, lane);
+                if (r < 0) break;                          // dependent on the basis: skipped
+                const uint32_t p = piv[r];
+                if (p != 0xFFFFu) {
+#pragma unroll
+                    for (int j = 0; j < WPL; ++j) v[j] ^= basis[((size_t)p * WPL + j) * 32 + lane];
+                    vc ^= coef[(size_t)p * 32 + lane];
+                } else {
+                    if (lane == (nb >> 5)) vc |= 1u << (nb & 31);
+#pragma unroll
+                    for (int j = 0; j < WPL; ++j) basis[((size_t)nb * WPL + j) * 32 + lane] = v[j];
+                    coef[(size_t)nb * 32 + lane] = vc;
+                    if (lane == 0) { piv[r] = (uint16_t)nb; col[nb] = c; }
+                    ++nb;
+                    __syncwarp();
+                    reduce_s();
+                    break;
+                }
+            }
+        }
+        if (done) {
+            // the error vector = the basis columns whose coefficient bit is set in sc
+            uint32_t *corr_row = a.corr_out ? a.corr_out + (size_t)shot * a.MW : nullptr;
+            if (corr_row) for (uint32_t w = lane; w < a.MW; w += 32) corr_row[w] = 0u;
+            __syncwarp();
+            uint32_t om = 0, bits = sc;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint32_t c = col[32 * lane + b];
+                om ^= a.var_obs[c];
+                if (corr_row) atomicXor(&corr_row[c >> 5], 1u << (c & 31u));
+            }
+            om = __reduce_xor_sync(0xffffffffu, om);
+            if (lane == 0) {
+                a.pred[(size_t)shot * a.OW] = om;
+                if (a.flags_out) a.flags_out[shot] = 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static int osd_wpl(uint32_t DW) { return DW <= 32 ? 1 : (DW <= 64 ? 2 : (DW <= 128 ? 4 : (DW <= 256 ? 8 : 0))); }
 
 int gq_bp_create(gq_dec *dec) {
     gq_dem *dem = dec->dem;
@@ -149,6 +371,9 @@ int gq_bp_create(gq_dec *dec) {
             }
         for (uint32_t m = 0; m < M; ++m) std::sort(var_edge.begin() + var_ptr[m], var_edge.begin() + var_ptr[m + 1]);
     }
+    // detectors of every variable (CSR by variable, ascending): the columns of H for OSD
+    std::vector<uint32_t> var_chk(dem->det_idx.begin(), dem->det_idx.end());
+    for (uint32_t m = 0; m < M; ++m) std::sort(var_chk.begin() + var_ptr[m], var_chk.begin() + var_ptr[m + 1]);
     std::vector<float> prior(M);
     for (uint32_t m = 0; m < M; ++m) {
         double p = std::min(std::max(dem->p[m], 1e-30), 1 - 1e-7);
@@ -164,15 +389,23 @@ int gq_bp_create(gq_dec *dec) {
     int rc;
     if ((rc = up(&dec->d_chk_ptr, chk_ptr)) || (rc = up(&dec->d_chk_var, chk_var)) ||
         (rc = up(&dec->d_var_ptr, var_ptr)) || (rc = up(&dec->d_var_edge, var_edge)) ||
-        (rc = up(&dec->d_var_obs, var_obs)))
+        (rc = up(&dec->d_var_obs, var_obs)) || (rc = up(&dec->d_var_chk, var_chk)))
         return rc;
+    if (dec->params.bp_osd) {
+        if (osd_wpl(dem->DW) == 0) GQ_FAIL(GQ_E_UNSUPPORTED, "BP+OSD: more than 8192 detectors are not supported");
+        const int osmem = 4 * (int)((D + 1) & ~1u) * 2;
+        cudaFuncSetAttribute(osd_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
+        cudaFuncSetAttribute(osd_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
+        cudaFuncSetAttribute(osd_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
+        cudaFuncSetAttribute(osd_solve_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
+    }
     GQ_CUDA(cudaMalloc((void **)&dec->d_prior, (size_t)M * 4));
     GQ_CUDA(cudaMemcpy(dec->d_prior, prior.data(), (size_t)M * 4, cudaMemcpyHostToDevice));
     dec->bp_msgs_per_block = ((size_t)nnz + M + 31) & ~(size_t)31;
     size_t bytes = dec->bp_msgs_per_block * 4;
     if (bytes <= 200 * 1024) {
         dec->bp_blocks = dem->num_sms * std::max<int>(1, std::min<int>(8, (int)(200 * 1024 / bytes)));
-        cudaFuncSetAttribute(bp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (cudaFuncSetAttribute(bp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024) != cudaSuccess) GQ_FAIL(GQ_E_CUDA, "BP decoder: cudaFuncSetAttribute failed");   // + 12 KB static (OSD selection)
     } else {
         dec->bp_blocks = dem->num_sms * 4;
         GQ_CUDA(cudaMalloc((void **)&dec->d_bp_msgs, bytes * dec->bp_blocks));
@@ -183,6 +416,7 @@ int gq_bp_create(gq_dec *dec) {
 void gq_bp_destroy(gq_dec *dec) {
     cudaFree(dec->d_chk_ptr); cudaFree(dec->d_chk_var); cudaFree(dec->d_var_ptr);
     cudaFree(dec->d_var_edge); cudaFree(dec->d_var_obs); cudaFree(dec->d_prior); cudaFree(dec->d_bp_msgs);
+    cudaFree(dec->d_var_chk); cudaFree(dec->d_osd_cand); cudaFree(dec->d_osd_fail); cudaFree(dec->d_osd_scratch);
 }
 
 int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
@@ -190,8 +424,6 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
     gq_dem *dem = dec->dem;
     BpArgs a;
     memset(&a, 0, sizeof(a));
-    a.dets = dets_sm; a.pred = pred_sm; a.iters_out = weight_out; a.flags_out = flags_out; a.corr_out = corr_out;
-    a.nshots = nshots;
     a.D = dem->D; a.M = dem->M; a.DW = dem->DW; a.OW = dem->OW; a.MW = (dem->M + 31) / 32; a.nnz = dec->bp_nnz;
     a.chk_ptr = dec->d_chk_ptr; a.chk_var = dec->d_chk_var; a.var_ptr = dec->d_var_ptr;
     a.var_edge = dec->d_var_edge; a.var_obs = dec->d_var_obs; a.prior = dec->d_prior;
@@ -199,9 +431,54 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
     a.max_iter = dec->params.bp_max_iter; a.alpha = dec->params.bp_alpha;
     a.use_shared = dec->d_bp_msgs == nullptr;
     size_t smem = a.use_shared ? dec->bp_msgs_per_block * 4 : 0;
-    int blocks = (int)std::min<uint64_t>(nshots, (uint64_t)dec->bp_blocks);
-    bp_kernel<<<blocks, 256, smem, dem->stream>>>(a);
-    GQ_CUDA(cudaGetLastError());
-    ++*launches;
+    const bool osd = dec->params.bp_osd != 0;
+    const uint64_t chunk = osd ? 16384 : nshots;       // OSD keeps 4 KB of candidates per unconverged shot
+    const int wpl = osd_wpl(dem->DW);
+    const int osd_blocks = dem->num_sms * 2, osd_warps = osd_blocks * 4;
+    const size_t osd_stride = (size_t)OSD_KMAX * (32 * (size_t)wpl + 32 + 1);
+    if (osd) {
+        if (!dec->d_osd_cand) {
+            GQ_CUDA(cudaMalloc((void **)&dec->d_osd_cand, chunk * OSD_KMAX * 4));
+            GQ_CUDA(cudaMalloc((void **)&dec->d_osd_fail, (chunk + 1) * 4));
+            GQ_CUDA(cudaMalloc((void **)&dec->d_osd_scratch, (size_t)osd_warps * osd_stride * 4));
+        }
+        a.osd_k = OSD_KMAX; a.cand = dec->d_osd_cand; a.fail_list = dec->d_osd_fail + 1; a.fail_count = dec->d_osd_fail;
+    }
+    for (uint64_t s0 = 0; s0 < nshots; s0 += chunk) {
+        const uint64_t ns = std::min(chunk, nshots - s0);
+        a.dets = dets_sm + s0 * dem->DW; a.pred = pred_sm + s0 * dem->OW;
+        a.iters_out = weight_out ? weight_out + s0 : nullptr;
+        a.flags_out = flags_out ? flags_out + s0 : nullptr;
+        a.corr_out = corr_out ? corr_out + s0 * a.MW : nullptr;
+        a.nshots = ns;
+        if (osd) GQ_CUDA(cudaMemsetAsync(dec->d_osd_fail, 0, 4, dem->stream));
+        int blocks = (int)std::min<uint64_t>(ns, (uint64_t)dec->bp_blocks);
+        bp_kernel<<<blocks, 256, smem, dem->stream>>>(a);
+        GQ_CUDA(cudaGetLastError());
+        ++*launches;
+        if (!osd) continue;
+        uint32_t nfail = 0;
+        GQ_CUDA(cudaMemcpyAsync(&nfail, dec->d_osd_fail, 4, cudaMemcpyDeviceToHost, dem->stream));
+        GQ_CUDA(cudaStreamSynchronize(dem->stream));
+        dec->osd_shots += nfail;
+        if (nfail == 0) continue;
+        OsdArgs o;
+        memset(&o, 0, sizeof(o));
+        o.dets = a.dets; o.pred = a.pred; o.flags_out = a.flags_out; o.corr_out = a.corr_out;
+        o.cand = dec->d_osd_cand; o.fail_list = dec->d_osd_fail + 1; o.nfail = nfail;
+        o.D = dem->D; o.DW = dem->DW; o.OW = dem->OW; o.MW = a.MW; o.M = dem->M;
+        o.var_ptr = dec->d_var_ptr; o.var_chk = dec->d_var_chk; o.var_obs = dec->d_var_obs;
+        o.scratch = dec->d_osd_scratch; o.scratch_stride = osd_stride;
+        const int ob = (int)std::min<uint32_t>((nfail + 3) / 4, (uint32_t)osd_blocks);
+        const size_t osmem = 4 * (size_t)((dem->D + 1) & ~1u) * 2;
+        switch (wpl) {
+        case 1: osd_solve_kernel<1><<<ob, 128, osmem, dem->stream>>>(o); break;
+        case 2: osd_solve_kernel<2><<<ob, 128, osmem, dem->stream>>>(o); break;
+        case 4: osd_solve_kernel<4><<<ob, 128, osmem, dem->stream>>>(o); break;
+        default: osd_solve_kernel<8><<<ob, 128, osmem, dem->stream>>>(o); break;
+        }
+        GQ_CUDA(cudaGetLastError());
+        ++*launches;
+    }
     return GQ_OK;
 }

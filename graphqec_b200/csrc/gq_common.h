@@ -97,6 +97,9 @@ struct gq_dec {
     uint32_t *d_chk_ptr = nullptr, *d_chk_var = nullptr, *d_var_ptr = nullptr, *d_var_edge = nullptr;
     float *d_prior = nullptr;
     uint32_t *d_var_obs = nullptr;
+    uint32_t *d_var_chk = nullptr;     // detectors of every variable (columns of H), for OSD
+    uint32_t *d_osd_cand = nullptr, *d_osd_fail = nullptr, *d_osd_scratch = nullptr;
+    uint64_t osd_shots = 0;            // shots handed to OSD so far
     float *d_bp_msgs = nullptr;
     size_t bp_msgs_per_block = 0;
     int bp_blocks = 0;

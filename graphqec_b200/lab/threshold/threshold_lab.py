@@ -32,8 +32,8 @@ __all__ = ["ThresholdLAB"]
 __available_decoders__ = {
     "pymatching": "matching",
     "fusion_blossom": "matching",
-    "bposd": "bp_minsum",
-    "bp_minsum": "bp_minsum",
+    "bposd": "bp_osd",          # min-sum BP, then OSD-0 on the shots BP leaves unconverged
+    "bp_minsum": "bp_minsum",   # BP alone (unconverged shots keep BP's last hard decision)
     "mwpf": None,
     "beliefmatching": None,
 }
@@ -152,9 +152,10 @@ class ThresholdLAB:
         family = __available_decoders__[self.decoder]
         if family is None:
             raise NotImplementedError(
-                f"decoder {self.decoder!r} has no B200 kernel; use 'pymatching' (exact matching) or 'bposd' (min-sum BP)"
+                f"decoder {self.decoder!r} has no B200 kernel; use 'pymatching' (exact matching), 'bposd' (min-sum BP + OSD-0) or 'bp_minsum'"
             )
         kind = be.MATCHING if family == "matching" else be.BP_MINSUM
+        bp_osd = family == "bp_osd"
         seed = int(opts.get("seed", DEFAULT_SEED))
         dist, rank, world = _dist_info()
         device = int(opts.get("device", _default_device(rank)))
@@ -195,6 +196,7 @@ class ThresholdLAB:
                     weight_levels=int(opts.get("weight_levels", 0)),
                     bp_max_iter=int(opts.get("bp_max_iter", 0)),
                     bp_alpha=float(opts.get("bp_alpha", 0.0)),
+                    bp_osd=bp_osd,
                 )
                 try:
                     shots, errors, discards = _run_task(

@@ -53,6 +53,8 @@ class B200Decoder(_DecoderBase):
     """``sinter.Decoder`` backed by the sm_100a kernels; ``kind`` = "matching" or "bp_minsum"."""
 
     def __init__(self, kind: str = "matching", device: int = 0, **params) -> None:
+        if kind == "bposd":
+            params.setdefault("bp_osd", True)     # BP, then OSD-0 where BP did not converge
         self.kind, self.device, self.params = _KINDS[kind], device, params
 
     def compile_decoder_for_dem(self, *, dem) -> B200CompiledDecoder:
@@ -78,6 +80,8 @@ class B200CompiledSampler(_CompiledSamplerBase):
 
 class B200Sampler(_SamplerBase):
     def __init__(self, kind: str = "matching", device: int = 0, seed: int = 20261019, **params) -> None:
+        if kind == "bposd":
+            params.setdefault("bp_osd", True)
         self.kind, self.device, self.seed, self.params = _KINDS[kind], device, seed, params
 
     def compiled_sampler_for_task(self, task) -> B200CompiledSampler:

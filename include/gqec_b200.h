@@ -50,7 +50,9 @@ typedef struct gq_decoder_params {
     int32_t bp_max_iter;       /* BP: iteration cap (default 30) */
     float bp_alpha;            /* BP: min-sum normalisation factor (default 0.9) */
     int32_t legacy_tiers;      /* matching: 1 = skip the first tier (A/B testing only) */
-    int32_t reserved[7];
+    int32_t bp_osd;            /* BP: 1 = order-0 ordered-statistics decoding (OSD-0) of the shots BP leaves
+                                  unconverged -- the "OSD" of the reference's decoder="bposd" (stimbposd) */
+    int32_t reserved[6];
 } gq_decoder_params;
 
 typedef struct gq_dem_info {

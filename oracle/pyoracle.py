@@ -60,6 +60,10 @@ def lib() -> ctypes.CDLL:
         L.orc_count_errors.argtypes = [c.c_void_p, c.c_void_p, c.c_long, c.c_int]
         L.orc_bp_minsum.restype = c.c_int
         L.orc_bp_minsum.argtypes = [c.c_int, c.c_int] + [c.c_void_p] * 6 + [c.c_int, c.c_float, c.c_void_p]
+        L.orc_bp_osd0.restype = c.c_int
+        L.orc_bp_osd0.argtypes = [c.c_int, c.c_int] + [c.c_void_p] * 6 + [c.c_int, c.c_float, c.c_int, c.c_int] + [c.c_void_p] * 4
+        L.orc_osd0.restype = c.c_int
+        L.orc_osd0.argtypes = [c.c_int, c.c_int] + [c.c_void_p] * 6 + [c.c_int, c.c_int] + [c.c_void_p] * 3
         _LIB = L
     return _LIB
 
@@ -250,6 +254,31 @@ class BpOracle:
             self.max_iter, ctypes.c_float(self.alpha), _p(out),
         )
         return out, it
+
+    def decode_osd(self, syndrome_bits: np.ndarray, max_candidates: int = 0, max_basis: int = 0):
+        """BP, then OSD-0 where BP did not converge: (error vector, BP iterations (negative = not converged),
+        OSD status (-1 not needed, 0 solved, 1 gave up), basis size, candidates walked)."""
+        syn = np.ascontiguousarray(syndrome_bits, dtype=np.uint8)
+        out = np.zeros(self.dem.num_errors, dtype=np.uint8)
+        st, nb, used = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        it = lib().orc_bp_osd0(
+            self.dem.num_detectors, self.dem.num_errors, _p(self.chk_indptr), _p(self.chk_var),
+            _p(self.var_indptr), _p(self.var_edge), _p(self.prior), _p(syn),
+            self.max_iter, ctypes.c_float(self.alpha), int(max_candidates), int(max_basis), _p(out),
+            ctypes.byref(st), ctypes.byref(nb), ctypes.byref(used),
+        )
+        return out, it, st.value, nb.value, used.value
+
+    def osd0(self, posterior: np.ndarray, syndrome_bits: np.ndarray, max_candidates: int = 0, max_basis: int = 0):
+        """OSD-0 alone on a given posterior: (status, error vector)."""
+        syn = np.ascontiguousarray(syndrome_bits, dtype=np.uint8)
+        post = np.ascontiguousarray(posterior, dtype=np.float32)
+        out = np.zeros(self.dem.num_errors, dtype=np.uint8)
+        rc = lib().orc_osd0(
+            self.dem.num_detectors, self.dem.num_errors, _p(self.chk_indptr), _p(self.chk_var),
+            _p(self.var_indptr), _p(self.var_edge), _p(post), _p(syn), int(max_candidates), int(max_basis), _p(out), None, None,
+        )
+        return rc, out
 
 
 def wilson(errors: int, shots: int, z: float = 1.959963984540054) -> tuple[float, float]:

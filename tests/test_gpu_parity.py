@@ -386,6 +386,60 @@ def test_bp_matches_oracle_bit_for_bit(name, nshots):
     assert nconv > 0.5 * nshots
 
 
+@pytest.mark.parametrize("name,nshots,iters", [("rot3", 400, 4), ("steane", 400, 3), ("rot5", 150, 6), ("toric4", 150, 8)])
+def test_bp_osd_matches_oracle_bit_for_bit(name, nshots, iters):
+    """BP (few iterations, so that many shots stay unconverged) + OSD-0: the same error vector as
+    oracle/bp_oracle.c::orc_bp_osd0 on every shot, and every solved shot reproduces its syndrome."""
+    dem, demh, _ = case(name)
+    bp = be.DecoderHandle(demh, be.BP_MINSUM, bp_max_iter=iters, bp_alpha=0.9, bp_osd=True)
+    orc = po.BpOracle(dem, max_iter=iters, alpha=0.9)
+    dets, obs = demh.sample(23, 0, nshots)
+    pred, it_gpu, flags, corr = bp.decode(dets, want_weights=True, want_flags=True, want_corrections=True)
+    bits = np.unpackbits(b8(dets, dem.num_detectors), axis=1, bitorder="little")[:, : dem.num_detectors]
+    cb = np.unpackbits(corr.cpu().numpy().view(np.uint8).reshape(nshots, -1), axis=1, bitorder="little")[:, : dem.num_errors]
+    H, L = dem.dense_check_matrices()
+    it_gpu, flags = it_gpu.cpu().numpy(), flags.cpu().numpy()
+    n_osd = 0
+    for s in range(nshots):
+        e, it, st, nb, used = orc.decode_osd(bits[s], max_candidates=1024, max_basis=1024)
+        assert it == it_gpu[s]
+        assert (e == cb[s]).all(), (s, it, st)
+        assert flags[s] == (1 if st == 1 else 0)
+        if st != 1:
+            assert ((H @ cb[s]) % 2 == bits[s]).all()
+        n_osd += st == 0
+    assert n_osd >= 10
+    p32 = pred.cpu().numpy().view(np.uint32)[:, 0]
+    assert ((cb @ L.T) % 2 == (p32[:, None] & 1)).all()          # prediction = L.e, OSD shots included
+    # the throughput path (no flags / corrections requested) predicts the same
+    assert (bp.decode(dets) == pred).all()
+    bp.close()
+
+
+def test_bposd_decodes_the_bivariate_bicycle_code():
+    """decoder="bposd" end to end on BB [[72,12,6]]: with OSD every shot gets a valid correction, and the logical
+    error rate drops well below BP's alone"""
+    code = gq.BivariateBicycleCode(L1=6, L2=6, a1=3, a2=1, a3=2, b1=3, b2=1, b3=2, depolarize1_rate=0.003, depolarize2_rate=0.003)
+    code.build_memory_circuit(number_of_rounds=3, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model()
+    demh = be.DemHandle(dem, device=0)
+    n = 4 * demh.tile_shots
+    dets, obs = demh.sample(9, 0, n)
+    bp = be.DecoderHandle(demh, be.BP_MINSUM, bp_max_iter=30)
+    osd = be.DecoderHandle(demh, be.BP_MINSUM, bp_max_iter=30, bp_osd=True)
+    p0, _, f0 = bp.decode(dets, want_weights=True, want_flags=True)
+    p1, _, f1, corr = osd.decode(dets, want_weights=True, want_flags=True, want_corrections=True)
+    assert (f0 != 0).float().mean().item() > 0.02 and (f1 != 0).sum().item() == 0
+    H, L = dem.dense_check_matrices()
+    bits = np.unpackbits(b8(dets, dem.num_detectors), axis=1, bitorder="little")[:, : dem.num_detectors]
+    cb = np.unpackbits(corr.cpu().numpy().view(np.uint8).reshape(n, -1), axis=1, bitorder="little")[:, : dem.num_errors]
+    assert (((cb.astype(np.int32) @ H.T.astype(np.int32)) % 2) == bits).all()      # every correction reproduces its syndrome
+    e0 = (p0 != obs).any(dim=1).float().mean().item()
+    e1 = (p1 != obs).any(dim=1).float().mean().item()
+    assert e1 < 0.5 * e0
+    bp.close(); osd.close(); demh.close()
+
+
 def test_bp_on_bivariate_bicycle_code():
     """BASELINE configs[4] in miniature: BB [[72,12,6]], hyperedge DEM, min-sum BP through the fused path."""
     code = gq.BivariateBicycleCode(L1=6, L2=6, a1=3, a2=1, a3=2, b1=3, b2=1, b3=2, depolarize1_rate=0.001, depolarize2_rate=0.001)

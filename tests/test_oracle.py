@@ -273,3 +273,86 @@ def test_tree_tier_reports_undecodable_syndromes(tree_hostsim):
     dets = np.packbits(np.array([[1, 1, 0], [0, 0, 1], [1, 0, 1]], np.uint8), axis=1, bitorder="little")
     pred, wt, rc = _tree_decode(tree_hostsim, orc, dets)
     assert rc.tolist() == [0, 1, 1] and wt[0] == 5
+
+
+# ------------------------------------------------------------------------------------------
+# OSD-0 (oracle/bp_oracle.c::orc_osd0) against the textbook definition
+# ------------------------------------------------------------------------------------------
+
+def _osd0_textbook(H, post, syn):
+    """full OSD-0: greedy basis of ALL of H's column space in posterior order, then solve H_S x = s"""
+    D, M = H.shape
+    order = sorted(range(M), key=lambda v: (float(post[v]), v))
+    rows = []       # reduced basis vectors as python ints: (vector, coefficient mask over chosen ordinals)
+    piv = {}
+    chosen = []
+    for c in order:
+        v = int("".join(str(int(b)) for b in H[::-1, c]), 2)
+        m = 0
+        while v:
+            r = (v & -v).bit_length() - 1
+            if r in piv:
+                bv, bm = rows[piv[r]]
+                v ^= bv; m ^= bm
+            else:
+                piv[r] = len(rows)
+                rows.append((v, m | (1 << len(chosen))))
+                chosen.append(c)
+                break
+    s = int("".join(str(int(b)) for b in syn[::-1]), 2)
+    m = 0
+    while s:
+        r = (s & -s).bit_length() - 1
+        if r not in piv:
+            return None
+        bv, bm = rows[piv[r]]
+        s ^= bv; m ^= bm
+    e = np.zeros(M, np.uint8)
+    for b, c in enumerate(chosen):
+        if (m >> b) & 1:
+            e[c] = 1
+    return e
+
+
+def test_osd0_oracle_equals_the_textbook_definition():
+    from graphqec_b200 import CssCode
+    Hs = np.array([[1, 1, 1, 1, 0, 0, 0], [0, 1, 1, 0, 1, 1, 0], [0, 0, 1, 1, 0, 1, 1]])
+    code = CssCode(Hx=Hs, Hz=Hs, depolarize1_rate=0.01, depolarize2_rate=0.01)
+    code.build_memory_circuit(number_of_rounds=3, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model()
+    H, L = dem.dense_check_matrices()
+    bp = po.BpOracle(dem, max_iter=20)
+    rng = np.random.default_rng(7)
+    solved = 0
+    for t in range(120):
+        e = (rng.random(dem.num_errors) < 0.02).astype(np.uint8)
+        syn = ((H @ e) % 2).astype(np.uint8)
+        post = (bp.prior + rng.normal(0, 3.0, dem.num_errors)).astype(np.float32)    # any posterior will do
+        if t % 3 == 0:
+            post = np.round(post)                                                     # plenty of ties
+        rc, got = bp.osd0(post, syn)
+        want = _osd0_textbook(H, post, syn)
+        assert (rc == 0) == (want is not None)
+        if want is not None:
+            solved += 1
+            assert (got == want).all() and (((H @ got) % 2) == syn).all()
+        # the bounded walk either gives the same answer or gives up
+        rc2, got2 = bp.osd0(post, syn, max_candidates=40, max_basis=16)
+        assert rc2 == 1 or (got2 == want).all()
+    assert solved > 100
+
+
+def test_bp_then_osd_always_reproduces_the_syndrome():
+    code = RotatedSurfaceCode(distance=3, depolarize1_rate=0.02, depolarize2_rate=0.02)
+    code.build_memory_circuit(number_of_rounds=3, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model()
+    H, L = dem.dense_check_matrices()
+    bp = po.BpOracle(dem, max_iter=10)
+    dets, _ = po.sample(dem, 5, 400)
+    bits = np.unpackbits(dets, axis=1, bitorder="little")[:, : dem.num_detectors]
+    used = 0
+    for s in range(400):
+        e, it, st, nb, cand = bp.decode_osd(bits[s])
+        assert st in (-1, 0) and (((H @ e) % 2) == bits[s]).all()
+        used += st == 0
+    assert used > 10
