@@ -150,14 +150,40 @@ __global__ void __launch_bounds__(256) bp_kernel(BpArgs a) {
                 float m1 = INFINITY, m2 = INFINITY;
                 uint32_t arg = 0xFFFFFFFFu;
                 int sg = 0, par = 0;
-                for (uint32_t k = b + lane; k < e; k += 32) {
-                    float t = tot[a.chk_var[k]];
-                    float m = t - c2v[k];
-                    float av = fabsf(m);
-                    sg ^= (m < 0.0f);
-                    par ^= (t < 0.0f);
-                    if (av < m1) { m2 = m1; m1 = av; arg = k; }
-                    else if (av < m2) m2 = av;
+                // rows of up to 256 edges (8 per lane) keep their variable->check messages in registers between
+                // the two sweeps and have all their gathers in flight at once (the kernel is latency-bound: the
+                // scratch of the resident blocks is far bigger than L2); longer rows take the plain loops
+                const bool cached = e - b <= 256u;
+                float mv[8];
+                if (cached) {
+                    uint32_t var[8];
+                    float tt[8], cc[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const uint32_t k = b + lane + 32u * j; var[j] = k < e ? a.chk_var[k] : 0u; }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const uint32_t k = b + lane + 32u * j; tt[j] = k < e ? tot[var[j]] : 0.0f; cc[j] = k < e ? c2v[k] : 0.0f; }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t k = b + lane + 32u * j;
+                        if (k < e) {
+                            const float t = tt[j], m = t - cc[j], av = fabsf(m);
+                            mv[j] = m;
+                            sg ^= (m < 0.0f);
+                            par ^= (t < 0.0f);
+                            if (av < m1) { m2 = m1; m1 = av; arg = k; }
+                            else if (av < m2) m2 = av;
+                        }
+                    }
+                } else {
+                    for (uint32_t k = b + lane; k < e; k += 32) {
+                        float t = tot[a.chk_var[k]];
+                        float m = t - c2v[k];
+                        float av = fabsf(m);
+                        sg ^= (m < 0.0f);
+                        par ^= (t < 0.0f);
+                        if (av < m1) { m2 = m1; m1 = av; arg = k; }
+                        else if (av < m2) m2 = av;
+                    }
                 }
                 sg = __reduce_xor_sync(0xffffffffu, (unsigned)sg);
                 par = __reduce_xor_sync(0xffffffffu, (unsigned)par);
@@ -169,21 +195,59 @@ __global__ void __launch_bounds__(256) bp_kernel(BpArgs a) {
 #pragma unroll
                 for (int o = 16; o; o >>= 1) g2 = fminf(g2, __shfl_xor_sync(0xffffffffu, g2, o));
                 if (par != sc && lane == 0) s_notconv = 1;
-                for (uint32_t k = b + lane; k < e; k += 32) {
-                    float m = tot[a.chk_var[k]] - c2v[k];
-                    float mag = (k == garg) ? g2 : g1;
-                    int s = sc ^ sg ^ (m < 0.0f);
-                    c2v[k] = a.alpha * (s ? -mag : mag);
+                if (cached) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t k = b + lane + 32u * j;
+                        if (k < e) {
+                            const float mag = (k == garg) ? g2 : g1;
+                            const int sgn = sc ^ sg ^ (mv[j] < 0.0f);
+                            c2v[k] = a.alpha * (sgn ? -mag : mag);
+                        }
+                    }
+                } else {
+                    for (uint32_t k = b + lane; k < e; k += 32) {
+                        float m = tot[a.chk_var[k]] - c2v[k];
+                        float mag = (k == garg) ? g2 : g1;
+                        int s = sc ^ sg ^ (m < 0.0f);
+                        c2v[k] = a.alpha * (s ? -mag : mag);
+                    }
                 }
             }
             __syncthreads();
             if (it > 1 && s_notconv == 0) { converged = 1; used = it - 1; break; }
             if (it == a.max_iter + 1) { used = a.max_iter; break; }
             // ---- variable pass
-            for (uint32_t v = tid; v < a.M; v += blockDim.x) {
-                float t = a.prior[v];
-                for (uint32_t k = a.var_ptr[v]; k < a.var_ptr[v + 1]; ++k) t += c2v[a.var_edge[k]];
-                tot[v] = t;
+            // (two variables per thread at a time, edge ids and messages of four edges of each in flight; every
+            // sum keeps the oracle's order)
+            for (uint32_t v = tid; v < a.M; v += 2 * blockDim.x) {
+                const uint32_t v2 = v + blockDim.x;
+                const bool has2 = v2 < a.M;
+                float t1 = a.prior[v], t2 = has2 ? a.prior[v2] : 0.0f;
+                const uint32_t b1 = a.var_ptr[v], e1 = a.var_ptr[v + 1];
+                const uint32_t b2 = has2 ? a.var_ptr[v2] : 0u, e2 = has2 ? a.var_ptr[v2 + 1] : 0u;
+                const uint32_t n = max(e1 - b1, e2 - b2);
+                for (uint32_t o = 0; o < n; o += 4) {
+                    uint32_t ed1[4], ed2[4];
+                    float c1[4], c2[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        ed1[j] = b1 + o + j < e1 ? a.var_edge[b1 + o + j] : 0u;
+                        ed2[j] = b2 + o + j < e2 ? a.var_edge[b2 + o + j] : 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        c1[j] = b1 + o + j < e1 ? c2v[ed1[j]] : 0.0f;
+                        c2[j] = b2 + o + j < e2 ? c2v[ed2[j]] : 0.0f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (b1 + o + j < e1) t1 += c1[j];
+                        if (b2 + o + j < e2) t2 += c2[j];
+                    }
+                }
+                tot[v] = t1;
+                if (has2) tot[v2] = t2;
             }
             __syncthreads();
         }
@@ -407,7 +471,7 @@ int gq_bp_create(gq_dec *dec) {
         dec->bp_blocks = dem->num_sms * std::max<int>(1, std::min<int>(8, (int)(200 * 1024 / bytes)));
         if (cudaFuncSetAttribute(bp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024) != cudaSuccess) GQ_FAIL(GQ_E_CUDA, "BP decoder: cudaFuncSetAttribute failed");   // + 12 KB static (OSD selection)
     } else {
-        dec->bp_blocks = dem->num_sms * 4;
+        dec->bp_blocks = dem->num_sms * 5;   // 48 registers: five blocks of 256 threads per SM
         GQ_CUDA(cudaMalloc((void **)&dec->d_bp_msgs, bytes * dec->bp_blocks));
     }
     return GQ_OK;
