@@ -324,6 +324,9 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
 #ifndef GQ_MT_PER_SM_K4
 #define GQ_MT_PER_SM_K4 4
 #endif
+#ifndef GQ_MT_PER_SM_K56
+#define GQ_MT_PER_SM_K56 2
+#endif
 #ifndef GQ_SIDE_STREAMS
 #define GQ_SIDE_STREAMS 0   // 1: the smaller classes' kernels run on side streams (overlapping tails, but co-resident
                             // kernels share the instruction cache: measured slower once start/solve were split)
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 4 ? 8 : (K <=
 // throughput instantiation leaves that code out, which is worth it because the kernel is at the edge of
 // the instruction cache
 template <int K, bool EXTRAS>
-__global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? 2 : 1)))) tree_solve_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? GQ_MT_PER_SM_K56 : 1)))) tree_solve_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -520,7 +523,7 @@ static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, i
     const int blocks_a = (int)std::min<uint64_t>((b.nitems + WPB - 1) / WPB, (uint64_t)dem->num_sms * 8);   // latency-bound: all 64 warps/SM
     tree_start_kernel<K><<<blocks_a, 32 * WPB, WPB * sizeof(StartWarpMem<K>), st>>>(b);
     if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
-    const int per_sm = K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? 2 : 1));
+    const int per_sm = K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? GQ_MT_PER_SM_K56 : 1));
     const int blocks_b = (int)std::min<uint64_t>((b.nitems + WPB - 1) / WPB, (uint64_t)dem->num_sms * per_sm);
     if (ev0) cudaEventRecord(ev0, st);   // bench.py's roofline times the solve kernel of the biggest class
     if (b.weight_out || b.flags_out || b.corr_out) tree_solve_kernel<K, true><<<blocks_b, 32 * WPB, WPB * sizeof(MtWarpMem<K>), st>>>(b);
