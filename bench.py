@@ -34,11 +34,11 @@ SEED = 20261019
 WORKLOAD = "RotatedSurfaceCode d=11 r=11 p=0.005 Z-memory (BASELINE configs[1], north-star point)"
 ALG_BYTES_PER_SHOT = (1320 + 1) / 8.0   # bit-packed syndrome + observable per shot
 # from the committed ncu --set full capture of the dominant kernel (profiles/, this round); None = not captured
-# profiles/r01_tree_solve_kernel3_v7_summary.txt: 464.8 MB read + 7.9 MB written / 767 034 shots (the hand-off
-# records are ~6 B per defect + 16 B of that), 3.525e9 warp-instructions, 69.6 % of issue slots active
-NCU_DRAM_BYTES_PER_SHOT = (464.817664e6 + 7.941120e6) / 767034
-NCU_WARP_INSTR_PER_SHOT = 3524586766 / 767034
-NCU_ISSUE_ACTIVE_PCT = 69.6
+# profiles/r01_tree_solve_kernel3_v8_summary.txt: 465.4 MB read + 7.1 MB written / 767 034 shots (the hand-off
+# records are ~6 B per defect + 16 B of that), 3.446e9 warp-instructions, 69.5 % of issue slots active
+NCU_DRAM_BYTES_PER_SHOT = (465.435904e6 + 7.081728e6) / 767034
+NCU_WARP_INSTR_PER_SHOT = 3446326842 / 767034
+NCU_ISSUE_ACTIVE_PCT = 69.5
 
 
 _JSON_FD = None
