@@ -1,6 +1,6 @@
 // K3a, first tier: one shot per warp, no materialised weight matrix.
 //
-// decode_shot<K>() takes the defect list of one shot (32*(K-1) < n <= 32*K defects, ascending
+// decode_shot<K>() takes the defect list of one shot (n <= 32*K defects, K = 1..8, 10, 12, 16, 24, 32; ascending
 // detector index) and returns the exact minimum-weight matching's observable prediction:
 //   1. nearest other defect of every defect: the 16 nearest detectors of its detector (a static sorted
 //      list) are tested against the syndrome bits in shared memory; the few defects with no fired
@@ -44,11 +44,6 @@ typedef unsigned __int128 gqw_mask;   // one bit per slot; the single host lane 
 typedef unsigned gqw_mask;
 #endif
 #define GQW_FULL 0xffffffffu
-#ifndef GQ_AP_UNROLL
-#define GQ_AP_UNROLL 2   // rows of the all-pairs pass in flight per warp
-#endif
-#define GQ_PRAGMA_STR(x) _Pragma(#x)
-#define GQ_PRAGMA_UNROLL(n) GQ_PRAGMA_STR(unroll n)
 #define GQW_BIT(k) ((gqw_mask)1 << (k))
 
 #ifdef GQ_MT_STATS

@@ -750,9 +750,10 @@ int gq_matching_create(gq_dec *dec) {
         GQ_CUDA(cudaMalloc((void **)&dec->d_adj_edge, std::max<size_t>(adj_edge.size(), 1) * 4));
         GQ_CUDA(cudaMemcpy(dec->d_adj_edge, adj_edge.data(), adj_edge.size() * 4, cudaMemcpyHostToDevice));
     }
-    // ---- tiers: register-resident solver with K = 1, 2, 4, 8 slots per lane (< 32K defects); the
-    // first pass uses the smallest tier that holds mu + 4 sigma defects, stragglers climb the ladder
-    // through overflow lists and anything beyond 255 defects falls to the memory-resident solver
+    // ---- the older ladder (shots beyond the first tier's 1024 defects, shots it gives up on, legacy_tiers = 1):
+    // dense-matrix register-resident solver with K = 1, 2, 4, 8 slots per lane (< 32K defects); the first pass
+    // uses the smallest tier that holds mu + 4 sigma defects, stragglers climb the ladder through overflow
+    // lists and anything beyond 255 defects falls to the memory-resident solver
     {
         double want = mu + 2.5 * sqrt(2 * mu + 1);
         if (dec->params.fast_capacity > 0) want = dec->params.fast_capacity;

@@ -20,13 +20,15 @@ CONFIGS = [
     ("UnrotatedSurfaceCode", {"distance": 5}, 0.008, 100000),
     ("RotatedSurfaceCode", {"distance": 9}, 0.005, 200000),
     ("RotatedSurfaceCode", {"distance": 11}, 0.005, 600000),
+    ("RotatedSurfaceCode", {"distance": 11}, 0.005, 2400000),    # the north-star point, tighter interval
+    ("RotatedSurfaceCode", {"distance": 11}, 0.008, 300000),     # 129 defects per shot: classes K = 4 .. 6
 ]
 nthreads = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_ler.json")
 res = json.load(open(path)) if os.path.exists(path) else []
-have = {(r["code"], json.dumps(r["kwargs"]), r["p"]) for r in res}
+have = {(r["code"], json.dumps(r["kwargs"]), r["p"], r["shots"]) for r in res}
 for cname, kw, p, shots in CONFIGS:
-    if (cname, json.dumps(kw), p) in have:
+    if (cname, json.dumps(kw), p, shots) in have:
         continue
     code = getattr(gq, cname)(**kw, depolarize1_rate=p, depolarize2_rate=p)
     code.build_memory_circuit(number_of_rounds=code.distance, logic_check="Z")
