@@ -459,3 +459,29 @@ def test_bp_on_bivariate_bicycle_code():
     shots, errors, _ = bp.collect(3, 0, n, 0)
     assert shots == n and errors == int((pred != obs).any(dim=1).sum().item())
     bp.close(); demh.close()
+
+
+# ------------------------------------------------------------------------------------------ edges of the input space
+def test_empty_single_zero_and_saturated_batches():
+    """0 shots, 1 shot, all-zero and all-one syndromes (padding bits beyond D set) through both decoders"""
+    import torch
+    dem, demh, dech = case("rot3")
+    bp = be.DecoderHandle(demh, be.BP_MINSUM, bp_max_iter=2, bp_osd=True)
+    empty = torch.zeros((0, demh.DW), dtype=torch.int32, device="cuda")
+    assert tuple(dech.decode(empty).shape) == (0, demh.OW) and tuple(bp.decode(empty).shape) == (0, demh.OW)
+    assert dech.decode_b8(np.zeros((0, (dem.num_detectors + 7) // 8), np.uint8)).shape == (0, 1)
+    one, _ = demh.sample(1, 0, 1)
+    assert tuple(dech.decode(one).shape) == (1, demh.OW)
+    assert dech.collect(1, 0, 1, 0)[0] == 1 and bp.collect(1, 0, demh.tile_shots, 0)[0] == demh.tile_shots
+    zeros = torch.zeros((5, demh.DW), dtype=torch.int32, device="cuda")
+    assert not dech.decode(zeros).any() and not bp.decode(zeros).any()
+    ones = torch.full((3, demh.DW), -1, dtype=torch.int32, device="cuda")
+    pred, wts, flags = dech.decode(ones, want_weights=True, want_flags=True)
+    orc, _ = oracle_for(dem, dech)
+    _, owts = orc.decode_batch(b8(ones, dem.num_detectors), return_weights=True)
+    assert (flags == 0).all() and (wts.cpu().numpy() == owts).all()
+    pb, ib, fb, cb = bp.decode(ones, want_weights=True, want_flags=True, want_corrections=True)
+    H, _ = dem.dense_check_matrices()
+    bits = np.unpackbits(cb.cpu().numpy().view(np.uint8).reshape(3, -1), axis=1, bitorder="little")[:, : dem.num_errors]
+    assert (fb == 0).all() and (((bits @ H.T) % 2) == 1).all()       # OSD found a correction for the all-ones syndrome
+    bp.close()
