@@ -2,7 +2,7 @@
 //
 // decode_shot<K>() takes the defect list of one shot (n <= 32*K defects, K = 1..8, 10, 12, 16, 24, 32; ascending
 // detector index) and returns the exact minimum-weight matching's observable prediction:
-//   1. nearest other defect of every defect: the 16 nearest detectors of its detector (a static sorted
+//   1. nearest other defect of every defect: the NBR_LEN = 12 nearest detectors of its detector (a static sorted
 //      list) are tested against the syndrome bits in shared memory; the few defects with no fired
 //      detector among them take a full row of the L2-resident distance table instead;
 //   2. dual start y(v) = min(nearest/2, boundary distance): a vertex whose boundary is at least as
@@ -72,7 +72,10 @@ struct Tables {
                            // index whose syndrome word is the always-zero word behind the row)
 };
 
-static constexpr int NBR_LEN = 16;
+#ifndef GQ_NBR_LEN
+#define GQ_NBR_LEN 12   // measured at the north star: 8 -> 37.5, 12 -> 36.8, 16 -> 37.8, 24 -> 39.1 ms per 2^22 shots
+#endif
+static constexpr int NBR_LEN = GQ_NBR_LEN;   // a multiple of 4 (16-byte loads)
 static constexpr int SYN_WORDS = 256;   // syndrome rows up to this many words are mirrored in shared memory
 
 // ---- defect list of one bit-packed syndrome row (ascending detector index); returns the count,

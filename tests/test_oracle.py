@@ -183,7 +183,14 @@ def _device_tables(orc):
     return dist, pobs
 
 
-def _neighbor_lists(dist, D, DW, L=16):
+def _nbr_len():
+    import re
+    src = open(os.path.join(ROOT, "graphqec_b200", "csrc", "match_tree.cuh")).read()
+    return int(re.search(r"#define GQ_NBR_LEN (\d+)", src).group(1))
+
+
+def _neighbor_lists(dist, D, DW, L=None):
+    L = L or _nbr_len()
     """nearest-detector lists as matching.cu builds them: distance << 16 | detector, ascending, padded"""
     nbr = np.full((D + 2, L), (0xFFFF << 16) | (32 * DW), np.uint32)
     for s in range(D):
