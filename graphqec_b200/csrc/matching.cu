@@ -413,13 +413,14 @@ struct StartRecord {
     uint32_t n, pad[3];
 };
 
+// Per-warp shared memory of the start kernel, laid out at run time so that it is as small as the syndrome allows
+// (what is not shared memory is L1 for the nearest-detector lists and the distance rows):
+//   def u16[32 K] | xch i16[32 K] | synw u32[SW + 1] | spre u16[SW + 2]      (SW = DW when the syndrome is mirrored, else 0)
 template <int K>
-struct StartWarpMem {
-    uint32_t synw[gqt::SYN_WORDS + 1];
-    uint16_t spre[gqt::SYN_WORDS + 2];
-    uint16_t def[32 * K];
-    int16_t xch[32 * K];
-};
+static size_t start_warp_bytes(uint32_t DW) {
+    const uint32_t sw = DW <= (uint32_t)gqt::SYN_WORDS ? DW : 0u;
+    return ((size_t)32 * K * 4 + ((size_t)sw + 1) * 4 + ((size_t)sw + 2) * 2 + 15) & ~(size_t)15;
+}
 
 template <int K>
 __global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 4 ? 8 : (K <= 6 ? 4 : (K <= 8 ? 3 : 1)))) tree_start_kernel(MatchArgs a) {
@@ -427,15 +428,20 @@ __global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 4 ? 8 : (K <=
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    StartWarpMem<K> &M = reinterpret_cast<StartWarpMem<K> *>(smem)[wib];
+    const bool mirror = a.nbr != nullptr && a.DW <= (uint32_t)gqt::SYN_WORDS;
+    const uint32_t sw = mirror ? a.DW : 0u;
+    char *wbase = smem + (size_t)wib * ((32u * K * 4 + (sw + 1) * 4 + (sw + 2) * 2 + 15u) & ~15u);
+    uint16_t *m_def = reinterpret_cast<uint16_t *>(wbase);
+    int16_t *m_xch = reinterpret_cast<int16_t *>(wbase + 32 * K * 2);
+    uint32_t *m_synw = reinterpret_cast<uint32_t *>(wbase + 32 * K * 4);
+    uint16_t *m_spre = reinterpret_cast<uint16_t *>(wbase + 32 * K * 4 + (sw + 1) * 4);
     StartRecord<K> *recs = reinterpret_cast<StartRecord<K> *>(a.ws);
     gqt::Tables T;
     T.dist = a.dist; T.pobs = a.pobs; T.D = a.D; T.N = a.N; T.nbr = a.nbr;
-    const bool mirror = a.nbr != nullptr && a.DW <= (uint32_t)gqt::SYN_WORDS;
     for (uint32_t item = warp; item < a.nitems; item += nwarps) {
         const uint32_t shot = a.list[item];
-        const int n0 = gqt::extract_defects(a.dets + (size_t)shot * a.DW, a.DW, a.D, lane, M.def, 32 * K,
-                                            mirror ? M.synw : nullptr, M.spre);
+        const int n0 = gqt::extract_defects(a.dets + (size_t)shot * a.DW, a.DW, a.D, lane, m_def, 32 * K,
+                                            mirror ? m_synw : nullptr, m_spre);
         StartRecord<K> &R = recs[item];
         if (n0 > 32 * K || n0 <= MtClassRange<K>::LO) {   // the list lied about the defect count: the solver will hand it on
             if (lane == 0) R.n = 0xffffffffu;
@@ -444,11 +450,11 @@ __global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 4 ? 8 : (K <=
         }
         gqt::i32 yb[K];
         int m0[K];
-        gqt::dual_start<K>(T, M.xch, M.def, n0, lane, mirror ? M.synw : nullptr, M.spre, yb, m0);
+        gqt::dual_start<K>(T, m_xch, m_def, n0, lane, mirror ? m_synw : nullptr, m_spre, yb, m0);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int v = lane + 32 * k;
-            if (v < n0) { R.def[v] = M.def[v]; R.yh[v] = (uint16_t)(yb[k] >> 1); R.mate[v] = (int16_t)m0[k]; }
+            if (v < n0) { R.def[v] = m_def[v]; R.yh[v] = (uint16_t)(yb[k] >> 1); R.mate[v] = (int16_t)m0[k]; }
         }
         if (lane == 0) R.n = (uint32_t)n0;
         __syncwarp();
@@ -521,7 +527,7 @@ template <int K>
 static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, int *launches, cudaEvent_t ev0, cudaEvent_t ev1) {
     constexpr int WPB = MtClassRange<K>::WPB;
     const int blocks_a = (int)std::min<uint64_t>((b.nitems + WPB - 1) / WPB, (uint64_t)dem->num_sms * 8);   // latency-bound: all 64 warps/SM
-    tree_start_kernel<K><<<blocks_a, 32 * WPB, WPB * sizeof(StartWarpMem<K>), st>>>(b);
+    tree_start_kernel<K><<<blocks_a, 32 * WPB, WPB * start_warp_bytes<K>(b.DW), st>>>(b);
     if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
     const int per_sm = K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? GQ_MT_PER_SM_K56 : 1));
     const int blocks_b = (int)std::min<uint64_t>((b.nitems + WPB - 1) / WPB, (uint64_t)dem->num_sms * per_sm);
@@ -536,7 +542,7 @@ static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, i
 
 template <int K>
 static int configure_tree_class() {
-    if (cudaFuncSetAttribute(tree_start_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MtClassRange<K>::WPB * sizeof(StartWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
+    if (cudaFuncSetAttribute(tree_start_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MtClassRange<K>::WPB * start_warp_bytes<K>(gqt::SYN_WORDS))) != cudaSuccess) return GQ_E_CUDA;
     if (cudaFuncSetAttribute(tree_solve_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MtClassRange<K>::WPB * sizeof(MtWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
     if (cudaFuncSetAttribute(tree_solve_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MtClassRange<K>::WPB * sizeof(MtWarpMem<K>))) != cudaSuccess) return GQ_E_CUDA;
     return GQ_OK;
