@@ -324,6 +324,9 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
 #ifndef GQ_MT_PER_SM_K4
 #define GQ_MT_PER_SM_K4 4
 #endif
+#ifndef GQ_MT_OVERSUB
+#define GQ_MT_OVERSUB 1   // solve-kernel blocks per resident slot (> 1: the block scheduler balances the tail)
+#endif
 #ifndef GQ_MT_PER_SM_K56
 #define GQ_MT_PER_SM_K56 2
 #endif
@@ -530,7 +533,7 @@ static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, i
     tree_start_kernel<K><<<blocks_a, 32 * WPB, WPB * start_warp_bytes<K>(b.DW), st>>>(b);
     if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
     const int per_sm = K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? GQ_MT_PER_SM_K56 : 1));
-    const int blocks_b = (int)std::min<uint64_t>((b.nitems + WPB - 1) / WPB, (uint64_t)dem->num_sms * per_sm);
+    const int blocks_b = (int)std::min<uint64_t>((b.nitems + WPB - 1) / WPB, (uint64_t)dem->num_sms * per_sm * GQ_MT_OVERSUB);
     if (ev0) cudaEventRecord(ev0, st);   // bench.py's roofline times the solve kernel of the biggest class
     if (b.weight_out || b.flags_out || b.corr_out) tree_solve_kernel<K, true><<<blocks_b, 32 * WPB, WPB * sizeof(MtWarpMem<K>), st>>>(b);
     else tree_solve_kernel<K, false><<<blocks_b, 32 * WPB, WPB * sizeof(MtWarpMem<K>), st>>>(b);
