@@ -51,6 +51,8 @@ struct SampleArgs {
     const GqClass *classes;
     const uint32_t *seg_first;
     const uint32_t *mech_ptr, *mech_det, *mech_obs, *mech_orig;
+    const uint4 *mech_rec;   // nullable: one 16-byte record per mechanism {det0 | det1 << 16, det2 | det3 << 16, observable
+                             // mask, detector count} when every mechanism has <= 4 detectors below 65536 (one load per hit)
     uint32_t nclasses, nsegments;
     uint32_t D, DW, OW, T, Tlog2;
     uint64_t seed, tile0, nshots;  // tile0 = global index of the first tile of this call
@@ -97,13 +99,23 @@ __global__ void __launch_bounds__(256) sample_kernel(SampleArgs a) {
                     const uint32_t m = c.mech_start + (pos >> a.Tlog2);
                     const uint32_t s = pos & (a.T - 1);
                     uint32_t *row = tile + s * stride;
-                    const uint32_t b = a.mech_ptr[m], e = a.mech_ptr[m + 1];
-                    for (uint32_t q = b; q < e; ++q) {
-                        uint32_t d = a.mech_det[q];
-                        atomicXor(&row[d >> 5], 1u << (d & 31));
+                    if (a.mech_rec) {
+                        const uint4 rec = a.mech_rec[m];
+                        const uint32_t d0 = rec.x & 0xffffu, d1 = rec.x >> 16, d2 = rec.y & 0xffffu, d3 = rec.y >> 16;
+                        if (rec.w > 0) atomicXor(&row[d0 >> 5], 1u << (d0 & 31));
+                        if (rec.w > 1) atomicXor(&row[d1 >> 5], 1u << (d1 & 31));
+                        if (rec.w > 2) atomicXor(&row[d2 >> 5], 1u << (d2 & 31));
+                        if (rec.w > 3) atomicXor(&row[d3 >> 5], 1u << (d3 & 31));
+                        if (rec.z) atomicXor(&row[a.DW], rec.z);
+                    } else {
+                        const uint32_t b = a.mech_ptr[m], e = a.mech_ptr[m + 1];
+                        for (uint32_t q = b; q < e; ++q) {
+                            uint32_t d = a.mech_det[q];
+                            atomicXor(&row[d >> 5], 1u << (d & 31));
+                        }
+                        const uint32_t om = a.mech_obs[m];
+                        if (om) atomicXor(&row[a.DW], om);
                     }
-                    const uint32_t om = a.mech_obs[m];
-                    if (om) atomicXor(&row[a.DW], om);
                     if (a.errs) {
                         uint64_t gs = shot_base + s;
                         if (gs < a.nshots)
@@ -319,6 +331,24 @@ extern "C" int gq_dem_create(uint32_t D, uint32_t O, uint32_t M, const double *p
     }
     dem->nclasses = (uint32_t)classes.size();
     dem->nsegments = nseg;
+    // one-load records for the sampler when every mechanism is small enough
+    std::vector<uint32_t> mech_rec;
+    {
+        bool ok = D < 65536u;
+        for (size_t i = 0; ok && i + 1 < mech_ptr.size(); ++i) ok = mech_ptr[i + 1] - mech_ptr[i] <= 4;
+        if (ok) {
+            mech_rec.assign(4 * (mech_ptr.size() - 1), 0u);
+            for (size_t i = 0; i + 1 < mech_ptr.size(); ++i) {
+                const uint32_t b = mech_ptr[i], n = mech_ptr[i + 1] - b;
+                uint32_t d[4] = {0, 0, 0, 0};
+                for (uint32_t q = 0; q < n; ++q) d[q] = mech_det[b + q];
+                mech_rec[4 * i + 0] = d[0] | (d[1] << 16);
+                mech_rec[4 * i + 1] = d[2] | (d[3] << 16);
+                mech_rec[4 * i + 2] = mech_obs[i];
+                mech_rec[4 * i + 3] = n;
+            }
+        }
+    }
     // ---- transposed CSR for the bit-sliced extractor
     std::vector<uint32_t> row_ptr(D + O + 1, 0), row_mech(dem->det_idx.size() + dem->obs_idx.size());
     for (uint32_t d : dem->det_idx) row_ptr[d + 1]++;
@@ -335,6 +365,7 @@ extern "C" int gq_dem_create(uint32_t D, uint32_t O, uint32_t M, const double *p
     if ((rc = upload(&dem->d_classes, classes)) || (rc = upload(&dem->d_seg_first, seg_first)) ||
         (rc = upload(&dem->d_mech_ptr, mech_ptr)) || (rc = upload(&dem->d_mech_det, mech_det)) ||
         (rc = upload(&dem->d_mech_obs, mech_obs)) || (rc = upload(&dem->d_mech_orig, mech_orig)) ||
+        (!mech_rec.empty() && (rc = upload(&dem->d_mech_rec, mech_rec))) ||
         (rc = upload(&dem->d_row_ptr, row_ptr)) || (rc = upload(&dem->d_row_mech, row_mech))) {
         gq_dem_destroy(dem);
         return rc;
@@ -348,7 +379,7 @@ extern "C" void gq_dem_destroy(gq_dem *dem) {
     if (!dem) return;
     cudaSetDevice(dem->device);
     cudaFree(dem->d_classes); cudaFree(dem->d_seg_first); cudaFree(dem->d_mech_ptr);
-    cudaFree(dem->d_mech_det); cudaFree(dem->d_mech_obs); cudaFree(dem->d_mech_orig);
+    cudaFree(dem->d_mech_det); cudaFree(dem->d_mech_obs); cudaFree(dem->d_mech_orig); cudaFree(dem->d_mech_rec);
     cudaFree(dem->d_row_ptr); cudaFree(dem->d_row_mech);
     if (dem->stream) cudaStreamDestroy(dem->stream);
     delete dem;
@@ -374,6 +405,7 @@ extern "C" int gq_sample(gq_dem *dem, uint64_t seed, uint64_t shot0, uint64_t ns
     a.classes = dem->d_classes; a.seg_first = dem->d_seg_first;
     a.mech_ptr = dem->d_mech_ptr; a.mech_det = dem->d_mech_det; a.mech_obs = dem->d_mech_obs;
     a.mech_orig = dem->d_mech_orig;
+    a.mech_rec = reinterpret_cast<const uint4 *>(dem->d_mech_rec);
     a.nclasses = dem->nclasses; a.nsegments = dem->nsegments;
     a.D = dem->D; a.DW = dem->DW; a.OW = dem->OW; a.T = dem->tile_shots; a.Tlog2 = dem->tile_log2;
     a.seed = seed; a.tile0 = shot0 / dem->tile_shots; a.nshots = nshots;
