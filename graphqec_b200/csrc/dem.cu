@@ -51,6 +51,8 @@ struct SampleArgs {
     const GqClass *classes;
     const uint32_t *seg_first;
     const uint32_t *mech_ptr, *mech_det, *mech_obs, *mech_orig;
+    const uint4 *seg_rec;    // [nsegments] {1 / log(1 - p) as float bits, first mechanism of the class, first and
+                             // one-past-last flat index of the segment}: one load instead of a binary search
     const uint4 *mech_rec;   // nullable: one 16-byte record per mechanism {det0 | det1 << 16, det2 | det3 << 16, observable
                              // mask, detector count} when every mechanism has <= 4 detectors below 65536 (one load per hit)
     uint32_t nclasses, nsegments;
@@ -72,15 +74,10 @@ __global__ void __launch_bounds__(256) sample_kernel(SampleArgs a) {
         const uint64_t gtile = a.tile0 + tl;
         const uint64_t shot_base = (uint64_t)tl * a.T;  // relative to this call's first shot
         for (uint32_t seg = threadIdx.x; seg < a.nsegments; seg += blockDim.x) {
-            // class lookup: last c with seg_first[c] <= seg
-            uint32_t lo = 0, hi = a.nclasses;
-            while (hi - lo > 1) {
-                uint32_t mid = (lo + hi) >> 1;
-                if (a.seg_first[mid] <= seg) lo = mid; else hi = mid;
-            }
-            const GqClass c = a.classes[lo];
-            uint32_t pos = (seg - c.seg_first) * c.seg_len;
-            const uint32_t end = min(pos + c.seg_len, c.flat_size);
+            const uint4 sr = a.seg_rec[seg];
+            struct { float inv_log1m; uint32_t mech_start; } c = {__uint_as_float(sr.x), sr.y};
+            uint32_t pos = sr.z;
+            const uint32_t end = sr.w;
             uint32_t draw = 0;
             bool done = false;
             while (!done) {
@@ -331,6 +328,18 @@ extern "C" int gq_dem_create(uint32_t D, uint32_t O, uint32_t M, const double *p
     }
     dem->nclasses = (uint32_t)classes.size();
     dem->nsegments = nseg;
+    // one record per RNG segment
+    std::vector<uint32_t> seg_rec((size_t)4 * nseg);
+    for (const GqClass &c : classes) {
+        const uint32_t ns = (c.flat_size + c.seg_len - 1) / c.seg_len;
+        for (uint32_t k = 0; k < ns; ++k) {
+            uint32_t bits;
+            memcpy(&bits, &c.inv_log1m, 4);
+            const uint32_t pos = k * c.seg_len;
+            uint32_t *r = &seg_rec[(size_t)4 * (c.seg_first + k)];
+            r[0] = bits; r[1] = c.mech_start; r[2] = pos; r[3] = std::min(pos + c.seg_len, c.flat_size);
+        }
+    }
     // one-load records for the sampler when every mechanism is small enough
     std::vector<uint32_t> mech_rec;
     {
@@ -365,7 +374,7 @@ extern "C" int gq_dem_create(uint32_t D, uint32_t O, uint32_t M, const double *p
     if ((rc = upload(&dem->d_classes, classes)) || (rc = upload(&dem->d_seg_first, seg_first)) ||
         (rc = upload(&dem->d_mech_ptr, mech_ptr)) || (rc = upload(&dem->d_mech_det, mech_det)) ||
         (rc = upload(&dem->d_mech_obs, mech_obs)) || (rc = upload(&dem->d_mech_orig, mech_orig)) ||
-        (!mech_rec.empty() && (rc = upload(&dem->d_mech_rec, mech_rec))) ||
+        (!mech_rec.empty() && (rc = upload(&dem->d_mech_rec, mech_rec))) || (rc = upload(&dem->d_seg_rec, seg_rec)) ||
         (rc = upload(&dem->d_row_ptr, row_ptr)) || (rc = upload(&dem->d_row_mech, row_mech))) {
         gq_dem_destroy(dem);
         return rc;
@@ -379,7 +388,7 @@ extern "C" void gq_dem_destroy(gq_dem *dem) {
     if (!dem) return;
     cudaSetDevice(dem->device);
     cudaFree(dem->d_classes); cudaFree(dem->d_seg_first); cudaFree(dem->d_mech_ptr);
-    cudaFree(dem->d_mech_det); cudaFree(dem->d_mech_obs); cudaFree(dem->d_mech_orig); cudaFree(dem->d_mech_rec);
+    cudaFree(dem->d_mech_det); cudaFree(dem->d_mech_obs); cudaFree(dem->d_mech_orig); cudaFree(dem->d_mech_rec); cudaFree(dem->d_seg_rec);
     cudaFree(dem->d_row_ptr); cudaFree(dem->d_row_mech);
     if (dem->stream) cudaStreamDestroy(dem->stream);
     delete dem;
@@ -406,6 +415,7 @@ extern "C" int gq_sample(gq_dem *dem, uint64_t seed, uint64_t shot0, uint64_t ns
     a.mech_ptr = dem->d_mech_ptr; a.mech_det = dem->d_mech_det; a.mech_obs = dem->d_mech_obs;
     a.mech_orig = dem->d_mech_orig;
     a.mech_rec = reinterpret_cast<const uint4 *>(dem->d_mech_rec);
+    a.seg_rec = reinterpret_cast<const uint4 *>(dem->d_seg_rec);
     a.nclasses = dem->nclasses; a.nsegments = dem->nsegments;
     a.D = dem->D; a.DW = dem->DW; a.OW = dem->OW; a.T = dem->tile_shots; a.Tlog2 = dem->tile_log2;
     a.seed = seed; a.tile0 = shot0 / dem->tile_shots; a.nshots = nshots;

@@ -57,6 +57,7 @@ struct gq_dem {
     uint32_t *d_mech_det = nullptr;    // [nnz]
     uint32_t *d_mech_obs = nullptr;    // [M] observable mask
     uint32_t *d_mech_orig = nullptr;   // [M] original mechanism index
+    uint32_t *d_seg_rec = nullptr;     // [nsegments][4] one-load segment records of the sampler
     uint32_t *d_mech_rec = nullptr;    // [M][4] one-load sampler records (null when a mechanism has > 4 detectors)
     // device: transposed CSR (row = detector, then observables) for the bit-sliced extractor
     uint32_t *d_row_ptr = nullptr;     // [D + O + 1]
