@@ -324,6 +324,9 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
 #ifndef GQ_MT_PER_SM_K4
 #define GQ_MT_PER_SM_K4 4
 #endif
+#ifndef GQ_START_PER_SM
+#define GQ_START_PER_SM 5   // start-kernel blocks per SM for K <= 4 (51 registers; measured: 8 -> 36.75, 6 -> 36.45, 5 -> 36.35 ms)
+#endif
 #ifndef GQ_MT_OVERSUB
 #define GQ_MT_OVERSUB 1   // solve-kernel blocks per resident slot (> 1: the block scheduler balances the tail)
 #endif
@@ -426,7 +429,7 @@ static size_t start_warp_bytes(uint32_t DW) {
 }
 
 template <int K>
-__global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 4 ? 8 : (K <= 6 ? 4 : (K <= 8 ? 3 : 1)))) tree_start_kernel(MatchArgs a) {
+__global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 4 ? GQ_START_PER_SM : (K <= 6 ? 4 : (K <= 8 ? 3 : 1)))) tree_start_kernel(MatchArgs a) {
     extern __shared__ __align__(16) char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
