@@ -72,6 +72,11 @@ struct Tables {
                            // index whose syndrome word is the always-zero word behind the row)
 };
 
+#ifndef GQ_FP2_MAXK
+#define GQ_FP2_MAXK 3   // classes up to this K try the second-event fast path: from K = 4 on its code costs more in
+                      // instruction-cache misses (hit rate 83 % at K = 4) than it saves (measured: K >= 4 without it -1.7 % at the
+                      // north star, -7 % at p = 0.008)
+#endif
 #ifndef GQ_NBR_LEN
 #define GQ_NBR_LEN 12   // measured at the north star: 8 -> 37.5, 12 -> 36.8, 16 -> 37.8, 24 -> 39.1 ms per 2^22 shots
 #endif
@@ -305,8 +310,8 @@ __device__ __forceinline__ int solve_tree(FT &f, const u16 *__restrict__ dist, c
                     // boundary -- the two or three new mates and duals are written directly.  Candidates, with the
                     // source in the type bits: 0 root -> k (the offers above), 1 w0 -> k, 2 the edge root - w0 turning
                     // tight (a blossom: left to the tree code), 3 boundary of root / w0.
-                    const int w0 = f.top[v0] == v0 ? (int)f.mate[v0] : -1;
-                    if (((best0 >> VB) & 3) == 0 && w0 >= 0 && f.top[w0] == w0) {
+                    const int w0 = (K <= GQ_FP2_MAXK && f.top[v0] == v0) ? (int)f.mate[v0] : -1;
+                    if (K <= GQ_FP2_MAXK && ((best0 >> VB) & 3) == 0 && w0 >= 0 && f.top[w0] == w0) {
                         const i32 t1 = (i32)(best0 >> TS);
                         i32 yw, wb4;
                         GQT_SEL(yb, w0, yw);

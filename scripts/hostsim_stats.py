@@ -8,7 +8,7 @@ from oracle import pyoracle as po
 import test_oracle as to
 
 so = os.path.join(ROOT, "tests", "hostsim", "libmthostsim.so")
-subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "tests", "hostsim", "mt_hostsim.cpp")] + sys.argv[2:])
+subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-DGQ_FP2_MAXK=1000000", "-o", so, os.path.join(ROOT, "tests", "hostsim", "mt_hostsim.cpp")] + sys.argv[2:])
 lib = ctypes.CDLL(so)
 lib.hostsim_mt_decode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_long] + [ctypes.c_void_p] * 5
 lib.hostsim_mt_stats.argtypes = [ctypes.c_void_p, ctypes.c_int]

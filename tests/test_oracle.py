@@ -160,7 +160,7 @@ def tree_hostsim(request):
     srcs = [os.path.join(ROOT, "tests", "hostsim", f) for f in ("mt_hostsim.cpp", "warp_sim.h")]
     srcs += [os.path.join(ROOT, "graphqec_b200", "csrc", f) for f in ("match_tree.cuh", "blossom_regs.cuh")]
     if not os.path.exists(so) or max(os.path.getmtime(s) for s in srcs) > os.path.getmtime(so):
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", f"-DHS_CAP={cap}", "-o", so, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", f"-DHS_CAP={cap}", "-DGQ_FP2_MAXK=1000000", "-o", so, srcs[0]])   # the one-lane build has K = cap: keep the second-event fast path in
     lib = ctypes.CDLL(so)
     lib.hostsim_mt_decode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_long] + [ctypes.c_void_p] * 5
