@@ -485,3 +485,38 @@ def test_empty_single_zero_and_saturated_batches():
     bits = np.unpackbits(cb.cpu().numpy().view(np.uint8).reshape(3, -1), axis=1, bitorder="little")[:, : dem.num_errors]
     assert (fb == 0).all() and (((bits @ H.T) % 2) == 1).all()       # OSD found a correction for the all-ones syndrome
     bp.close()
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_north_star_corrections_at_scale():
+    """Size-independent properties at the BASELINE size (2^20 shots of the north-star DEM, far beyond what the
+    oracle can decode in a test): every correction reproduces its shot's syndrome (H_graph . c == s), the prediction
+    is L . c, the reported weight is the weight of the correction, and the throughput path predicts the same."""
+    import torch
+    dem, demh, _ = case("rot11")
+    dech = be.DecoderHandle(demh, be.MATCHING, with_corrections=True)
+    u, v, w, om, pr = dech.edges()
+    E, D = len(u), dem.num_detectors
+    dev = torch.device("cuda")
+    inc = torch.zeros((E, D + 2), dtype=torch.float16, device=dev)         # columns D, D+1: observable bit, edge weight slot
+    inc[torch.arange(E), torch.from_numpy(u.astype(np.int64))] = 1
+    inner = np.flatnonzero(v != be.NO_DET)
+    inc[torch.from_numpy(inner), torch.from_numpy(v[inner].astype(np.int64))] = 1
+    inc[:, D] = torch.from_numpy((om & np.uint64(1)).astype(np.float16)).to(dev)
+    wt_vec = torch.from_numpy(w.astype(np.float32)).to(dev)
+    n, chunk = 1 << 20, 1 << 15
+    bad_syn = bad_obs = bad_wt = bad_fast = flagged = 0
+    shifts = torch.arange(32, device=dev, dtype=torch.int32)
+    for s0 in range(0, n, chunk):
+        dets, obs = demh.sample(77, s0, chunk)
+        pred, wts, flags, corr = dech.decode(dets, want_weights=True, want_flags=True, want_corrections=True)
+        flagged += int((flags != 0).sum().item())
+        cbits = ((corr.unsqueeze(-1) >> shifts) & 1).reshape(chunk, -1)[:, :E]
+        res = (cbits.to(torch.float16) @ inc).to(torch.int32)              # sums stay far below 2048: exact in fp16
+        sbits = ((dets.unsqueeze(-1) >> shifts) & 1).reshape(chunk, -1)[:, :D]
+        bad_syn += int(((res[:, :D] & 1) != sbits).any(dim=1).sum().item())
+        bad_obs += int(((res[:, D] & 1) != (pred[:, 0] & 1)).sum().item())
+        bad_wt += int(((cbits.to(torch.float32) @ wt_vec).to(torch.int64) != wts.to(torch.int64)).sum().item())
+        bad_fast += int((dech.decode(dets) != pred).any(dim=1).sum().item())
+    assert flagged == 0 and bad_syn == 0 and bad_obs == 0 and bad_wt == 0 and bad_fast == 0
+    dech.close()
