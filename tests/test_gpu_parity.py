@@ -554,3 +554,23 @@ def test_bb144_bposd_corrections_at_scale():
     assert int(((res[:, D] & 1) != (pred[:, 0] & 1)).sum().item()) == 0
     assert (pred != obs).any(dim=1).float().mean().item() < 0.01
     bp.close(); osd.close(); demh.close()
+
+
+@pytest.mark.parametrize("kind,d,p,nshots", [("UnrotatedSurfaceCode", 15, 0.003, 160), ("RotatedSurfaceCode", 17, 0.005, 96)])
+def test_large_codes_match_the_oracle(kind, d, p, nshots):
+    """BASELINE configs[2] (unrotated d = 15, 15 rounds: 6300 detectors, ~270 defects per shot) and a d = 17 point of the
+    reference's own example sweep (~330 defects): the wide classes of the first tier on natural syndromes give the
+    oracle's minimum weight, shot by shot."""
+    dem = make_dem(kind, p, distance=d)
+    demh = be.DemHandle(dem, device=0)
+    dech = be.DecoderHandle(demh, be.MATCHING)
+    dets, obs = demh.sample(3, 0, nshots)
+    pred, wts, flags = dech.decode(dets, want_weights=True, want_flags=True)
+    orc, _ = oracle_for(dem, dech)
+    d8 = b8(dets, dem.num_detectors)
+    nd = np.unpackbits(d8, axis=1, bitorder="little")[:, : dem.num_detectors].sum(1)
+    assert nd.mean() > 200 and nd.max() > 256                 # beyond the 8-bit classes
+    opred, owts = orc.decode_batch(d8, nthreads=8, return_weights=True)
+    assert (flags.cpu().numpy() == 0).all() and (wts.cpu().numpy() == owts).all()
+    assert (dech.decode(dets) == pred).all()
+    dech.close(); demh.close()
