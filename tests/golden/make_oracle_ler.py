@@ -22,6 +22,9 @@ CONFIGS = [
     ("RotatedSurfaceCode", {"distance": 11}, 0.005, 600000),
     ("RotatedSurfaceCode", {"distance": 11}, 0.005, 2400000),    # the north-star point, tighter interval
     ("RotatedSurfaceCode", {"distance": 11}, 0.008, 300000),     # 129 defects per shot: classes K = 4 .. 6
+    # BASELINE configs[3]: Steane code through CssCode, low-p tail (the matching graph ignores the hyperedges, as PyMatching does)
+    ("CssCode", {"Hx": [[1, 1, 1, 1, 0, 0, 0], [0, 1, 1, 0, 1, 1, 0], [0, 0, 1, 1, 0, 1, 1]],
+                 "Hz": [[1, 1, 1, 1, 0, 0, 0], [0, 1, 1, 0, 1, 1, 0], [0, 0, 1, 1, 0, 1, 1]]}, 0.001, 4000000),
 ]
 nthreads = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_ler.json")
@@ -30,7 +33,8 @@ have = {(r["code"], json.dumps(r["kwargs"]), r["p"], r["shots"]) for r in res}
 for cname, kw, p, shots in CONFIGS:
     if (cname, json.dumps(kw), p, shots) in have:
         continue
-    code = getattr(gq, cname)(**kw, depolarize1_rate=p, depolarize2_rate=p)
+    import numpy as np
+    code = getattr(gq, cname)(**{k: (np.array(v) if isinstance(v, list) else v) for k, v in kw.items()}, depolarize1_rate=p, depolarize2_rate=p)
     code.build_memory_circuit(number_of_rounds=code.distance, logic_check="Z")
     try:
         dem = code.memory_circuit.detector_error_model(decompose_errors=True)
