@@ -124,6 +124,23 @@ extern "C" int gq_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, 
     return decode_dispatch(dec, dets_sm, nshots, pred_sm, weight_out, flags_out, corr_out, &launches);
 }
 
+static int ensure_scratch(gq_dec *dec, uint64_t nshots);
+
+// detector-major in, detector-major out (32 shots per word): what the bit-sliced extractor (gq_extract) produces
+// and SURVEY 8b lists as gq_decode_dm.  Two bit-matrix transposes around gq_decode, in slices of the scratch size.
+extern "C" int gq_decode_dm(gq_dec *dec, const uint32_t *dets_dm, uint64_t nshots, uint32_t *pred_dm) {
+    if (!dec || !dets_dm || !pred_dm) GQ_FAIL(GQ_E_INVALID, "gq_decode_dm: NULL argument");
+    if (nshots == 0) return GQ_OK;
+    gq_dem *dem = dec->dem;
+    GQ_CUDA(cudaSetDevice(dem->device));
+    int rc = ensure_scratch(dec, nshots);
+    if (rc) return rc;
+    if ((rc = gq_transpose_dm_to_sm(dem, dets_dm, dem->D, nshots, dec->d_dets))) return rc;
+    int launches = 0;
+    if ((rc = decode_dispatch(dec, dec->d_dets, nshots, dec->d_pred, nullptr, nullptr, nullptr, &launches))) return rc;
+    return gq_transpose_sm_to_dm(dem, dec->d_pred, std::max<uint32_t>(dem->O, 1), nshots, pred_dm);
+}
+
 static int ensure_scratch(gq_dec *dec, uint64_t nshots) {
     if (dec->scratch_shots >= nshots) return GQ_OK;
     cudaFree(dec->d_dets); cudaFree(dec->d_obs); cudaFree(dec->d_pred);

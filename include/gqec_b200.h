@@ -153,6 +153,10 @@ int gq_decoder_get_edges(const gq_dec *dec, uint32_t *u, uint32_t *v, uint32_t *
 int gq_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
               int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out);
 
+/* ---- decode, device buffers in the detector-major bit-sliced layout of gq_extract (32 shots per word):
+ *      dets_dm: dev uint32[D][ceil(nshots/32)] -> pred_dm: dev uint32[max(O,1)][ceil(nshots/32)]. */
+int gq_decode_dm(gq_dec *dec, const uint32_t *dets_dm, uint64_t nshots, uint32_t *pred_dm);
+
 /* ---- decode, host buffers in sinter's layout: the body of
  *      CompiledDecoder.decode_shots_bit_packed(bit_packed_detection_event_data=...).
  *      dets_b8: host uint8[nshots][ceil(D/8)]; pred_b8: host uint8[nshots][ceil(O/8)]. */

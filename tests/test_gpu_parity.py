@@ -578,3 +578,14 @@ def test_large_codes_match_the_oracle(kind, d, p, nshots):
     assert (flags.cpu().numpy() == 0).all() and (wts.cpu().numpy() == owts).all()
     assert (dech.decode(dets) == pred).all()
     dech.close(); demh.close()
+
+
+def test_decode_dm_equals_decode_sm():
+    """gq_decode_dm (detector-major bit-sliced in / out, the layout of gq_extract) == gq_decode on the same shots"""
+    dem, demh, dech = case("rot5")
+    n = 3 * demh.tile_shots + 37
+    dets, obs = demh.sample(55, 0, n)
+    pred = dech.decode(dets)
+    dets_dm = demh.sm_to_dm(dets, demh.D, n)
+    pred_dm = dech.decode_dm(dets_dm, n)
+    assert (demh.dm_to_sm(pred_dm, 1, n) == pred).all()
