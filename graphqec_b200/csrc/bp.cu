@@ -54,20 +54,21 @@ struct BpArgs {
 };
 
 
-static constexpr int OSD_KMAX = 1024;     // candidates kept per shot (and the cap on the basis size)
+static constexpr int OSD_KMAX = 1024;     // cap on the basis size (one coefficient word per lane)
+static constexpr int OSD_NCAND = 2048;    // candidates kept per shot (BB-144 at p = 3e-3: up to ~1400 are walked, basis <= ~650)
 
 __device__ __forceinline__ uint32_t osd_key(float x) {   // order-preserving map float -> uint32
     const uint32_t b = __float_as_uint(x);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// The k variables with the smallest posterior, ascending (ties by index), written to out[0..k); k <= OSD_KMAX.
+// The k variables with the smallest posterior, ascending (ties by index), written to out[0..k); k <= OSD_NCAND.
 // All 256 threads of the block call it; tot[] holds the block's M posteriors.
 __device__ void osd_select(const float *tot, uint32_t M, uint32_t k, uint32_t *out) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_rank;
     __shared__ uint32_t cnt_less[256], cnt_tie[256];
-    __shared__ unsigned long long pairs[OSD_KMAX];
+    __shared__ unsigned long long pairs[OSD_NCAND];
     __shared__ uint32_t s_fill;
     const int tid = threadIdx.x;
     if (k > M) k = M;
@@ -98,7 +99,7 @@ __device__ void osd_select(const float *tot, uint32_t M, uint32_t k, uint32_t *o
     for (uint32_t v = lo; v < hi; ++v) { const uint32_t key = osd_key(tot[v]); nl += key < kth; nt += key == kth; }
     cnt_less[tid] = nl; cnt_tie[tid] = nt;
     if (tid == 0) s_fill = 0;
-    for (uint32_t i = tid; i < OSD_KMAX; i += 256) pairs[i] = ~0ull;
+    for (uint32_t i = tid; i < OSD_NCAND; i += 256) pairs[i] = ~0ull;
     __syncthreads();
     uint32_t tie_before = 0;
     for (int t = 0; t < tid; ++t) tie_before += cnt_tie[t];
@@ -110,9 +111,9 @@ __device__ void osd_select(const float *tot, uint32_t M, uint32_t k, uint32_t *o
     }
     __syncthreads();
     // ---- bitonic sort of the (key, index) pairs (padding sorts last)
-    for (uint32_t size = 2; size <= OSD_KMAX; size <<= 1) {
+    for (uint32_t size = 2; size <= OSD_NCAND; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t i = tid; i < OSD_KMAX / 2; i += 256) {
+            for (uint32_t i = tid; i < OSD_NCAND / 2; i += 256) {
                 const uint32_t a = 2 * i - (i & (stride - 1)), b = a + stride;
                 const bool up = (a & size) == 0;
                 const unsigned long long x = pairs[a], y = pairs[b];
@@ -121,7 +122,7 @@ __device__ void osd_select(const float *tot, uint32_t M, uint32_t k, uint32_t *o
             __syncthreads();
         }
     }
-    for (uint32_t i = tid; i < OSD_KMAX; i += 256) out[i] = i < k ? (uint32_t)pairs[i] : 0xFFFFFFFFu;
+    for (uint32_t i = tid; i < OSD_NCAND; i += 256) out[i] = i < k ? (uint32_t)pairs[i] : 0xFFFFFFFFu;
     __syncthreads();
 }
 
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(256) bp_kernel(BpArgs a) {
             __shared__ uint32_t s_slot;
             if (tid == 0) { s_slot = atomicAdd(a.fail_count, 1u); a.fail_list[s_slot] = (uint32_t)shot; }
             __syncthreads();
-            osd_select(tot, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_KMAX);
+            osd_select(tot, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_NCAND);
         }
     }
 }
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
     uint32_t *col = coef + (size_t)OSD_KMAX * 32;
     for (uint32_t item = warp; item < a.nfail; item += nwarps) {
         const uint32_t shot = a.fail_list[item];
-        const uint32_t *cand = a.cand + (size_t)item * OSD_KMAX;
+        const uint32_t *cand = a.cand + (size_t)item * OSD_NCAND;
         for (uint32_t r = lane; r < a.D; r += 32) piv[r] = 0xFFFFu;
         uint32_t s[WPL], sc = 0;
 #pragma unroll
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
             }
         };
         reduce_s();
-        for (uint32_t i = 0; i < OSD_KMAX && !done && nb < OSD_KMAX; ++i) {
+        for (uint32_t i = 0; i < OSD_NCAND && !done && nb < OSD_KMAX; ++i) {
             const uint32_t c = cand[i];
             if (c == 0xFFFFFFFFu) break;
             uint32_t v[WPL], vc = 0;
@@ -467,9 +468,9 @@ int gq_bp_create(gq_dec *dec) {
     GQ_CUDA(cudaMemcpy(dec->d_prior, prior.data(), (size_t)M * 4, cudaMemcpyHostToDevice));
     dec->bp_msgs_per_block = ((size_t)nnz + M + 31) & ~(size_t)31;
     size_t bytes = dec->bp_msgs_per_block * 4;
-    if (bytes <= 200 * 1024) {
-        dec->bp_blocks = dem->num_sms * std::max<int>(1, std::min<int>(8, (int)(200 * 1024 / bytes)));
-        if (cudaFuncSetAttribute(bp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024) != cudaSuccess) GQ_FAIL(GQ_E_CUDA, "BP decoder: cudaFuncSetAttribute failed");   // + 12 KB static (OSD selection)
+    if (bytes <= 192 * 1024) {
+        dec->bp_blocks = dem->num_sms * std::max<int>(1, std::min<int>(8, (int)(192 * 1024 / bytes)));
+        if (cudaFuncSetAttribute(bp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) GQ_FAIL(GQ_E_CUDA, "BP decoder: cudaFuncSetAttribute failed");   // + 19 KB static (OSD selection)
     } else {
         dec->bp_blocks = dem->num_sms * 5;   // 48 registers: five blocks of 256 threads per SM
         GQ_CUDA(cudaMalloc((void **)&dec->d_bp_msgs, bytes * dec->bp_blocks));
@@ -496,17 +497,17 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
     a.use_shared = dec->d_bp_msgs == nullptr;
     size_t smem = a.use_shared ? dec->bp_msgs_per_block * 4 : 0;
     const bool osd = dec->params.bp_osd != 0;
-    const uint64_t chunk = osd ? 16384 : nshots;       // OSD keeps 4 KB of candidates per unconverged shot
+    const uint64_t chunk = osd ? 16384 : nshots;       // OSD keeps 8 KB of candidates per unconverged shot
     const int wpl = osd_wpl(dem->DW);
     const int osd_blocks = dem->num_sms * 2, osd_warps = osd_blocks * 4;
     const size_t osd_stride = (size_t)OSD_KMAX * (32 * (size_t)wpl + 32 + 1);
     if (osd) {
         if (!dec->d_osd_cand) {
-            GQ_CUDA(cudaMalloc((void **)&dec->d_osd_cand, chunk * OSD_KMAX * 4));
+            GQ_CUDA(cudaMalloc((void **)&dec->d_osd_cand, chunk * OSD_NCAND * 4));
             GQ_CUDA(cudaMalloc((void **)&dec->d_osd_fail, (chunk + 1) * 4));
             GQ_CUDA(cudaMalloc((void **)&dec->d_osd_scratch, (size_t)osd_warps * osd_stride * 4));
         }
-        a.osd_k = OSD_KMAX; a.cand = dec->d_osd_cand; a.fail_list = dec->d_osd_fail + 1; a.fail_count = dec->d_osd_fail;
+        a.osd_k = OSD_NCAND; a.cand = dec->d_osd_cand; a.fail_list = dec->d_osd_fail + 1; a.fail_count = dec->d_osd_fail;
     }
     for (uint64_t s0 = 0; s0 < nshots; s0 += chunk) {
         const uint64_t ns = std::min(chunk, nshots - s0);

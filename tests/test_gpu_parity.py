@@ -405,7 +405,7 @@ def test_bp_osd_matches_oracle_bit_for_bit(name, nshots, iters):
     it_gpu, flags = it_gpu.cpu().numpy(), flags.cpu().numpy()
     n_osd = 0
     for s in range(nshots):
-        e, it, st, nb, used = orc.decode_osd(bits[s], max_candidates=1024, max_basis=1024)
+        e, it, st, nb, used = orc.decode_osd(bits[s], max_candidates=2048, max_basis=1024)
         assert it == it_gpu[s]
         assert (e == cb[s]).all(), (s, it, st)
         assert flags[s] == (1 if st == 1 else 0)
