@@ -93,7 +93,7 @@ struct gq_dec {
     uint32_t *d_overflow = nullptr;    // [1 + capacity] overflow shot list
     void *d_recs = nullptr;            // first tier: hand-off records between the start and the solve kernels
     size_t recs_bytes = 0;
-    uint32_t *d_lists = nullptr;       // first tier: [16] class counts, then one shot list per class
+    uint32_t *d_lists = nullptr;       // first tier: [64] class counts + work cursors, then one shot list per class
     uint32_t overflow_cap = 0;
     // ---- BP
     uint32_t *d_chk_ptr = nullptr, *d_chk_var = nullptr, *d_var_ptr = nullptr, *d_var_edge = nullptr;

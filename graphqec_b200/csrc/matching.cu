@@ -52,6 +52,7 @@ struct MatchArgs {
     size_t ws_stride;
     uint32_t *overflow;       // [0] count, [1] max defects, [2..] shots
     uint32_t overflow_cap;
+    uint32_t *cursor;         // first tier: next unclaimed item of the list (dynamic work distribution)
 };
 
 __device__ __forceinline__ void walk_path(const MatchArgs &a, uint32_t cur, uint32_t target, uint32_t *corr_row) {
@@ -350,6 +351,22 @@ template <int K> struct MtClassRange {     // defect counts a class-K list may h
     static constexpr int WPB = K <= 16 ? 8 : 4;   // warps per block: the K = 24, 32 forests are 30 .. 41 KB per warp
 };
 
+#ifndef GQ_DYNAMIC
+#define GQ_DYNAMIC 1   // 1: warps claim list items through an atomic cursor (shot times vary by an order of magnitude, so a
+                       // static grid-stride split leaves the SMs idle while the unluckiest warp finishes: sm__warps_active
+                       // was 88 % of its bound); 0: static grid-stride
+#endif
+// next item of a first-tier list for this warp; the first claim is the warp's own index (no atomic)
+__device__ __forceinline__ uint32_t mt_next_item(uint32_t *cursor, uint32_t nwarps, uint32_t item, int lane) {
+#if GQ_DYNAMIC
+    uint32_t nx = 0;
+    if (lane == 0) nx = nwarps + atomicAdd(cursor, 1u);
+    return __shfl_sync(0xffffffffu, nx, 0);
+#else
+    return item + nwarps;
+#endif
+}
+
 template <int K>
 struct MtWarpMem {
     gqr::StaticForest<32 * K> F;
@@ -444,7 +461,7 @@ __global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 4 ? GQ_START_
     StartRecord<K> *recs = reinterpret_cast<StartRecord<K> *>(a.ws);
     gqt::Tables T;
     T.dist = a.dist; T.pobs = a.pobs; T.D = a.D; T.N = a.N; T.nbr = a.nbr;
-    for (uint32_t item = warp; item < a.nitems; item += nwarps) {
+    for (uint32_t item = warp; item < a.nitems; item = mt_next_item(a.cursor, nwarps, item, lane)) {
         const uint32_t shot = a.list[item];
         const int n0 = gqt::extract_defects(a.dets + (size_t)shot * a.DW, a.DW, a.D, lane, m_def, 32 * K,
                                             mirror ? m_synw : nullptr, m_spre);
@@ -482,7 +499,7 @@ __global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 3 ? GQ_MT_PER
     T.dist = a.dist; T.pobs = a.pobs; T.D = a.D; T.N = a.N; T.nbr = a.nbr;
     const bool want_weight = EXTRAS && a.weight_out != nullptr;
 
-    for (uint32_t item = warp; item < a.nitems; item += nwarps) {
+    for (uint32_t item = warp; item < a.nitems; item = mt_next_item(a.cursor, nwarps, item, lane)) {
         const uint32_t shot = a.list[item];
         const StartRecord<K> &R = recs[item];
         const uint32_t n0u = R.n;
@@ -530,14 +547,16 @@ __global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 3 ? GQ_MT_PER
 }
 
 template <int K>
-static int launch_tree_class(const MatchArgs &b, gq_dem *dem, cudaStream_t st, int *launches, cudaEvent_t ev0, cudaEvent_t ev1) {
+static int launch_tree_class(MatchArgs b, uint32_t *cursors, gq_dem *dem, cudaStream_t st, int *launches, cudaEvent_t ev0, cudaEvent_t ev1) {
     constexpr int WPB = MtClassRange<K>::WPB;
+    b.cursor = cursors;   // [0]: start kernel, [16]: solve kernel (zeroed with the class counts)
     const int blocks_a = (int)std::min<uint64_t>((b.nitems + WPB - 1) / WPB, (uint64_t)dem->num_sms * 8);   // latency-bound: all 64 warps/SM
     tree_start_kernel<K><<<blocks_a, 32 * WPB, WPB * start_warp_bytes<K>(b.DW), st>>>(b);
     if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
     const int per_sm = K <= 3 ? GQ_MT_PER_SM : (K == 4 ? GQ_MT_PER_SM_K4 : (K <= 6 ? GQ_MT_PER_SM_K56 : 1));
     const int blocks_b = (int)std::min<uint64_t>((b.nitems + WPB - 1) / WPB, (uint64_t)dem->num_sms * per_sm * GQ_MT_OVERSUB);
     if (ev0) cudaEventRecord(ev0, st);   // bench.py's roofline times the solve kernel of the biggest class
+    b.cursor = cursors + 16;
     if (b.weight_out || b.flags_out || b.corr_out) tree_solve_kernel<K, true><<<blocks_b, 32 * WPB, WPB * sizeof(MtWarpMem<K>), st>>>(b);
     else tree_solve_kernel<K, false><<<blocks_b, 32 * WPB, WPB * sizeof(MtWarpMem<K>), st>>>(b);
     if (cudaGetLastError() != cudaSuccess) return GQ_E_CUDA;
@@ -782,7 +801,7 @@ int gq_matching_create(gq_dec *dec) {
         configure_tree_class<10>() || configure_tree_class<12>() || configure_tree_class<16>() ||
         configure_tree_class<24>() || configure_tree_class<32>())
         GQ_FAIL(GQ_E_CUDA, "matching decoder: cudaFuncSetAttribute failed for the first-tier kernels");
-    GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << GQ_SLICE_LOG2) + 16) * 4));
+    GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << GQ_SLICE_LOG2) + 64) * 4));
     for (int i = 0; i < MT_CLASSES - 1; ++i) {
         GQ_CUDA(cudaStreamCreateWithFlags(&dec->side_streams[i], cudaStreamNonBlocking));
         GQ_CUDA(cudaEventCreateWithFlags(&dec->side_done[i], cudaEventDisableTiming));
@@ -842,9 +861,9 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
         if (!dec->params.legacy_tiers) {
             // ---- first tier: per-K kernels over the lists classify_kernel builds (match_tree.cuh)
             uint32_t *d_counts = dec->d_lists;
-            uint32_t *d_lists = dec->d_lists + 16;
+            uint32_t *d_lists = dec->d_lists + 64;   // [0..16) class counts, [16..48) start / solve cursors
             GQ_CUDA(cudaMemsetAsync(ovf_buf[cur], 0, 8, dem->stream));
-            GQ_CUDA(cudaMemsetAsync(d_counts, 0, 16 * 4, dem->stream));
+            GQ_CUDA(cudaMemsetAsync(d_counts, 0, 64 * 4, dem->stream));
             ClassifyArgs ca;
             ca.dets = b.dets; ca.pred = b.pred; ca.weight_out = b.weight_out; ca.flags_out = b.flags_out;
             ca.counts = d_counts; ca.lists = d_lists; ca.list_stride = (uint32_t)slice;
@@ -884,19 +903,19 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
                 b.ws = (char *)dec->d_recs + rec_off[c]; b.ws_stride = start_record_bytes(c);
                 int lrc;
                 switch (c) {
-                case 0: lrc = launch_tree_class<1>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 1: lrc = launch_tree_class<2>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 2: lrc = launch_tree_class<3>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 3: lrc = launch_tree_class<4>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 4: lrc = launch_tree_class<5>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 5: lrc = launch_tree_class<6>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 6: lrc = launch_tree_class<7>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 7: lrc = launch_tree_class<8>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 8: lrc = launch_tree_class<10>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 9: lrc = launch_tree_class<12>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 10: lrc = launch_tree_class<16>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                case 11: lrc = launch_tree_class<24>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                default: lrc = launch_tree_class<32>(b, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 0: lrc = launch_tree_class<1>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 1: lrc = launch_tree_class<2>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 2: lrc = launch_tree_class<3>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 3: lrc = launch_tree_class<4>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 4: lrc = launch_tree_class<5>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 5: lrc = launch_tree_class<6>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 6: lrc = launch_tree_class<7>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 7: lrc = launch_tree_class<8>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 8: lrc = launch_tree_class<10>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 9: lrc = launch_tree_class<12>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 10: lrc = launch_tree_class<16>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 11: lrc = launch_tree_class<24>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                default: lrc = launch_tree_class<32>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 }
                 if (lrc) GQ_FAIL(lrc, "matching decoder: first-tier kernel launch failed");
                 if (st != dem->stream) {
