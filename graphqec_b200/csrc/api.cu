@@ -109,9 +109,10 @@ extern "C" int gq_decoder_get_edges(const gq_dec *dec, uint32_t *u, uint32_t *v,
 }
 
 static int decode_dispatch(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
-                           int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out, int *launches) {
+                           int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out, int *launches,
+                           bool preclassified = false) {
     if (dec->kind == GQ_DECODER_MATCHING)
-        return gq_matching_decode(dec, dets_sm, nshots, pred_sm, weight_out, flags_out, corr_out, launches);
+        return gq_matching_decode(dec, dets_sm, nshots, pred_sm, weight_out, flags_out, corr_out, launches, preclassified);
     return gq_bp_decode(dec, dets_sm, nshots, pred_sm, weight_out, flags_out, corr_out, launches);
 }
 
@@ -278,11 +279,15 @@ extern "C" int gq_collect(gq_dem *dem, gq_dec *dec, uint64_t seed, uint64_t shot
     while (done < nshots) {
         uint64_t ns = std::min(chunk, nshots - done);
         GQ_CUDA(cudaEventRecord(ev[0], dem->stream));
-        rc = gq_sample(dem, seed, shot0 + done, ns, dec->d_dets, dec->d_obs, nullptr);
+        // matching: the sampler sorts the shots it writes into the decoder's per-class lists (fused classification)
+        GqClassifyOut cls;
+        const bool fused_cls = dec->kind == GQ_DECODER_MATCHING && !dec->params.legacy_tiers;
+        if (fused_cls && (rc = gq_matching_classify_targets(dec, dec->d_pred, &cls))) return rc;
+        rc = gq_sample_classified(dem, seed, shot0 + done, ns, dec->d_dets, dec->d_obs, nullptr, fused_cls ? &cls : nullptr);
         if (rc) return rc;
         ++launches;
         GQ_CUDA(cudaEventRecord(ev[1], dem->stream));
-        rc = decode_dispatch(dec, dec->d_dets, ns, dec->d_pred, nullptr, nullptr, nullptr, &launches);
+        rc = decode_dispatch(dec, dec->d_dets, ns, dec->d_pred, nullptr, nullptr, nullptr, &launches, fused_cls);
         if (rc) return rc;
         GQ_CUDA(cudaEventRecord(ev[2], dem->stream));
         rc = gq_count_errors(dem, dec->d_pred, dec->d_obs, ns, dec->d_count);

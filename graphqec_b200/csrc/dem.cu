@@ -61,6 +61,7 @@ struct SampleArgs {
     uint32_t ntiles;
     uint32_t *dets, *obs, *errs;
     uint32_t err_words;  // ceil(nshots / 32)
+    GqClassifyOut cls;   // counts != null: sort the shots into the matching decoder's per-class lists while flushing
 };
 
 __global__ void __launch_bounds__(256) sample_kernel(SampleArgs a) {
@@ -128,9 +129,47 @@ __global__ void __launch_bounds__(256) sample_kernel(SampleArgs a) {
         const uint64_t rows_left = a.nshots - shot_base;
         const uint32_t rows = rows_left < a.T ? (uint32_t)rows_left : a.T;
         uint32_t *gd = a.dets + shot_base * a.DW;
-        for (uint32_t s0 = threadIdx.x / 32; s0 < rows; s0 += blockDim.x / 32) {
-            const uint32_t *row = tile + s0 * stride;
-            for (uint32_t w = threadIdx.x & 31; w < a.DW; w += 32) gd[(size_t)s0 * a.DW + w] = row[w];
+        if (a.cls.counts) {
+            // fused classification (what classify_kernel would do in a pass of its own): the defect count of every
+            // row is a popcount of words that are in shared memory anyway; the tile's shots are appended to the
+            // per-class lists with one global atomic per (tile, class)
+            uint32_t *cl_cnt = tile + tile_words;            // [16] shots of the tile per class (15 = overflow)
+            uint32_t *cl_base = cl_cnt + 16;                 // [16] their first position in the global lists
+            uint16_t *cl_pos = reinterpret_cast<uint16_t *>(cl_base + 16);   // [T] class << 12 | position within (tile, class)
+            if (threadIdx.x < 16) cl_cnt[threadIdx.x] = 0;
+            __syncthreads();
+            for (uint32_t s0 = threadIdx.x / 32; s0 < rows; s0 += blockDim.x / 32) {
+                const uint32_t *row = tile + s0 * stride;
+                uint32_t n = 0;
+                for (uint32_t w = threadIdx.x & 31; w < a.DW; w += 32) { const uint32_t v = row[w]; gd[(size_t)s0 * a.DW + w] = v; n += __popc(v); }
+                n = __reduce_add_sync(0xffffffffu, n);
+                if ((threadIdx.x & 31) == 0) {
+                    if (n == 0) {
+                        cl_pos[s0] = 0xffffu;
+                        for (uint32_t w = 0; w < a.cls.OW; ++w) a.cls.pred[(shot_base + s0) * a.cls.OW + w] = 0u;
+                    } else {
+                        const uint32_t c = (uint32_t)gq_mt_class_of((int)n);   // GQ_MT_CLASSES (13) = beyond the first tier
+                        cl_pos[s0] = (uint16_t)((c << 12) | atomicAdd(&cl_cnt[c], 1u));
+                        if (c == (uint32_t)GQ_MT_CLASSES) atomicMax(&a.cls.overflow[1], n);
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x <= (uint32_t)GQ_MT_CLASSES && cl_cnt[threadIdx.x])
+                cl_base[threadIdx.x] = atomicAdd(threadIdx.x < (uint32_t)GQ_MT_CLASSES ? &a.cls.counts[threadIdx.x] : &a.cls.overflow[0], cl_cnt[threadIdx.x]);
+            __syncthreads();
+            for (uint32_t s0 = threadIdx.x; s0 < rows; s0 += blockDim.x) {
+                const uint32_t cp = cl_pos[s0];
+                if (cp == 0xffffu) continue;
+                const uint32_t c = cp >> 12, at = cl_base[c] + (cp & 0xfffu);
+                if (c < (uint32_t)GQ_MT_CLASSES) a.cls.lists[(size_t)c * a.cls.list_stride + at] = (uint32_t)(shot_base + s0);
+                else if (at < a.cls.overflow_cap) a.cls.overflow[2 + at] = (uint32_t)(shot_base + s0);
+            }
+        } else {
+            for (uint32_t s0 = threadIdx.x / 32; s0 < rows; s0 += blockDim.x / 32) {
+                const uint32_t *row = tile + s0 * stride;
+                for (uint32_t w = threadIdx.x & 31; w < a.DW; w += 32) gd[(size_t)s0 * a.DW + w] = row[w];
+            }
         }
         if (a.obs) {
             uint32_t *go = a.obs + shot_base * a.OW;
@@ -406,6 +445,11 @@ extern "C" int gq_dem_get_info(const gq_dem *dem, gq_dem_info *info) {
 
 extern "C" int gq_sample(gq_dem *dem, uint64_t seed, uint64_t shot0, uint64_t nshots,
                          uint32_t *dets_sm, uint32_t *obs_sm, uint32_t *errs_mm) {
+    return gq_sample_classified(dem, seed, shot0, nshots, dets_sm, obs_sm, errs_mm, nullptr);
+}
+
+int gq_sample_classified(gq_dem *dem, uint64_t seed, uint64_t shot0, uint64_t nshots, uint32_t *dets_sm,
+                         uint32_t *obs_sm, uint32_t *errs_mm, const GqClassifyOut *cls) {
     if (!dem || !dets_sm) GQ_FAIL(GQ_E_INVALID, "gq_sample: NULL argument");
     if (shot0 % dem->tile_shots) GQ_FAIL(GQ_E_INVALID, "gq_sample: shot0 must be a multiple of tile_shots");
     if (nshots == 0) return GQ_OK;
@@ -424,13 +468,16 @@ extern "C" int gq_sample(gq_dem *dem, uint64_t seed, uint64_t shot0, uint64_t ns
     a.ntiles = (uint32_t)ntiles;
     a.dets = dets_sm; a.obs = obs_sm; a.errs = errs_mm;
     a.err_words = (uint32_t)((nshots + 31) / 32);
-    size_t smem = (size_t)dem->tile_shots * (dem->DW + dem->OW) * 4;
+    if (cls) a.cls = *cls;
+    if (a.cls.counts && (dem->tile_shots > 4096 || nshots > 0xFFFFFFFFull)) GQ_FAIL(GQ_E_INTERNAL, "gq_sample: classification limits");
+    size_t smem = (size_t)dem->tile_shots * (dem->DW + dem->OW) * 4 + 128 + (size_t)dem->tile_shots * 2;
     int per_sm = std::max<int>(1, (int)(200 * 1024 / std::max<size_t>(smem, 1)));
     per_sm = std::min(per_sm, 8);
     uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)dem->num_sms * per_sm);
     if (dem->nclasses == 0) {
         GQ_CUDA(cudaMemsetAsync(dets_sm, 0, nshots * dem->DW * 4, dem->stream));
         if (obs_sm) GQ_CUDA(cudaMemsetAsync(obs_sm, 0, nshots * dem->OW * 4, dem->stream));
+        if (a.cls.counts) GQ_CUDA(cudaMemsetAsync(a.cls.pred, 0, nshots * a.cls.OW * 4, dem->stream));   // every shot is defect-free
         return GQ_OK;
     }
     sample_kernel<<<grid, 256, smem, dem->stream>>>(a);

@@ -116,11 +116,37 @@ struct gq_dec {
     uint64_t b8_bytes = 0;
 };
 
+// first-tier classes of the matching decoder (matching.cu): K = ceil(defects / 32) slots per lane; classes 0..7: K = 1..8
+// (up to 256 defects), 8..10: K = 10, 12, 16 (up to 512), 11, 12: K = 24, 32 (up to 1024); GQ_MT_CLASSES = beyond the tier.
+// Shared with the sampler and the b8 re-stride kernel, which classify the shots they write (no separate pass).
+static constexpr int GQ_MT_CLASSES = 13;
+static constexpr int GQ_MT_CAP = 1024;
+__host__ __device__ constexpr int gq_mt_class_of(int n) {   // n >= 1 defects
+    return n <= 256 ? (n - 1) >> 5
+                    : (n <= 320 ? 8 : (n <= 384 ? 9 : (n <= 512 ? 10 : (n <= 768 ? 11 : (n <= 1024 ? 12 : GQ_MT_CLASSES)))));
+}
+struct GqClassifyOut {
+    uint32_t *counts = nullptr;     // [GQ_MT_CLASSES] shots per class (null: no classification)
+    uint32_t *lists = nullptr;      // [GQ_MT_CLASSES][list_stride] shot indices, relative to the call's first shot
+    uint32_t list_stride = 0;
+    uint32_t *overflow = nullptr;   // [0] count, [1] max defects, [2..] shots beyond the first tier
+    uint32_t overflow_cap = 0;
+    uint32_t *pred = nullptr;       // predictions: rows of defect-free shots are zeroed here
+    uint32_t OW = 0;
+};
+// dem.cu: gq_sample with the classification fused into the tile flush
+int gq_sample_classified(gq_dem *dem, uint64_t seed, uint64_t shot0, uint64_t nshots, uint32_t *dets_sm,
+                         uint32_t *obs_sm, uint32_t *errs_mm, const GqClassifyOut *cls);
+
 // matching.cu
 int gq_matching_create(gq_dec *dec);
+// zeroes the class counts / work cursors / overflow header of the next slice and says where a producer kernel
+// (sampler, re-stride) should append the shots; the following gq_matching_decode(..., preclassified = true) consumes them
+int gq_matching_classify_targets(gq_dec *dec, uint32_t *pred_sm, GqClassifyOut *out);
 void gq_matching_destroy(gq_dec *dec);
 int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
-                       int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out, int *launches);
+                       int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out, int *launches,
+                       bool preclassified = false);
 // bp.cu
 int gq_bp_create(gq_dec *dec);
 void gq_bp_destroy(gq_dec *dec);

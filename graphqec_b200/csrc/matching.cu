@@ -340,12 +340,9 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
 #endif
 // classes 0..7: K = 1..8 (8-bit vertex field, up to 256 defects); 8..10: K = 10, 12, 16 (9-bit field, up to 512);
 // 11, 12: K = 24, 32 (10-bit field, up to 1024; part of the per-lane state lives in local memory there)
-static constexpr int MT_CLASSES = 13;
-static constexpr int MT_CAP = 1024;
-__host__ __device__ constexpr int mt_class_of(int n) {   // n >= 1 defects -> class, MT_CLASSES = beyond the first tier
-    return n <= 256 ? (n - 1) >> 5
-                    : (n <= 320 ? 8 : (n <= 384 ? 9 : (n <= 512 ? 10 : (n <= 768 ? 11 : (n <= 1024 ? 12 : MT_CLASSES)))));
-}
+static constexpr int MT_CLASSES = GQ_MT_CLASSES;
+static constexpr int MT_CAP = GQ_MT_CAP;
+__host__ __device__ constexpr int mt_class_of(int n) { return gq_mt_class_of(n); }   // n >= 1 defects -> class, MT_CLASSES = beyond the first tier
 template <int K> struct MtClassRange {     // defect counts a class-K list may hold: (LO, 32 K]
     static constexpr int LO = K <= 8 ? 32 * (K - 1) : (K == 10 ? 256 : (K == 12 ? 320 : (K == 16 ? 384 : (K == 24 ? 512 : 768))));
     static constexpr int WPB = K <= 16 ? 8 : 4;   // warps per block: the K = 24, 32 forests are 30 .. 41 KB per warp
@@ -832,9 +829,25 @@ void gq_matching_destroy(gq_dec *dec) {
     if (dec->kev1) cudaEventDestroy(dec->kev1);
 }
 
-int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
-                       int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out, int *launches) {
+int gq_matching_classify_targets(gq_dec *dec, uint32_t *pred_sm, GqClassifyOut *out) {
     gq_dem *dem = dec->dem;
+    GQ_CUDA(cudaMemsetAsync(dec->d_overflow, 0, 8, dem->stream));
+    GQ_CUDA(cudaMemsetAsync(dec->d_lists, 0, 64 * 4, dem->stream));
+    out->counts = dec->d_lists;
+    out->lists = dec->d_lists + 64;
+    out->list_stride = 1u << GQ_SLICE_LOG2;
+    out->overflow = dec->d_overflow;
+    out->overflow_cap = dec->overflow_cap;
+    out->pred = pred_sm;
+    out->OW = dem->OW;
+    return GQ_OK;
+}
+
+int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
+                       int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out, int *launches, bool preclassified) {
+    gq_dem *dem = dec->dem;
+    if (preclassified && (nshots > (1ull << GQ_SLICE_LOG2) || dec->params.legacy_tiers))
+        GQ_FAIL(GQ_E_INTERNAL, "matching decoder: a pre-classified batch is one first-tier slice");
     if (corr_out && !dec->d_next) GQ_FAIL(GQ_E_INVALID, "gq_decode: corrections need with_corrections=1 at creation");
     MatchArgs a;
     memset(&a, 0, sizeof(a));
@@ -862,16 +875,18 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
             // ---- first tier: per-K kernels over the lists classify_kernel builds (match_tree.cuh)
             uint32_t *d_counts = dec->d_lists;
             uint32_t *d_lists = dec->d_lists + 64;   // [0..16) class counts, [16..48) start / solve cursors
-            GQ_CUDA(cudaMemsetAsync(ovf_buf[cur], 0, 8, dem->stream));
-            GQ_CUDA(cudaMemsetAsync(d_counts, 0, 64 * 4, dem->stream));
-            ClassifyArgs ca;
-            ca.dets = b.dets; ca.pred = b.pred; ca.weight_out = b.weight_out; ca.flags_out = b.flags_out;
-            ca.counts = d_counts; ca.lists = d_lists; ca.list_stride = (uint32_t)slice;
-            ca.overflow = ovf_buf[cur]; ca.overflow_cap = dec->overflow_cap;
-            ca.nshots = (uint32_t)ns; ca.D = a.D; ca.DW = a.DW; ca.OW = a.OW;
-            classify_kernel<<<(int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)dem->num_sms * 8), 256, 0, dem->stream>>>(ca);
-            GQ_CUDA(cudaGetLastError());
-            ++*launches;
+            if (!preclassified) {   // else the producer of the syndromes (sampler / re-stride kernel) has filled the lists
+                GQ_CUDA(cudaMemsetAsync(ovf_buf[cur], 0, 8, dem->stream));
+                GQ_CUDA(cudaMemsetAsync(d_counts, 0, 64 * 4, dem->stream));
+                ClassifyArgs ca;
+                ca.dets = b.dets; ca.pred = b.pred; ca.weight_out = b.weight_out; ca.flags_out = b.flags_out;
+                ca.counts = d_counts; ca.lists = d_lists; ca.list_stride = (uint32_t)slice;
+                ca.overflow = ovf_buf[cur]; ca.overflow_cap = dec->overflow_cap;
+                ca.nshots = (uint32_t)ns; ca.D = a.D; ca.DW = a.DW; ca.OW = a.OW;
+                classify_kernel<<<(int)std::min<uint64_t>((ns + 255) / 256, (uint64_t)dem->num_sms * 8), 256, 0, dem->stream>>>(ca);
+                GQ_CUDA(cudaGetLastError());
+                ++*launches;
+            }
             uint32_t counts[MT_CLASSES];
             GQ_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(counts), cudaMemcpyDeviceToHost, dem->stream));
             GQ_CUDA(cudaStreamSynchronize(dem->stream));
