@@ -57,10 +57,16 @@ def north_star_dem():
 
     code = RotatedSurfaceCode(distance=11, depolarize1_rate=0.005, depolarize2_rate=0.005)
     code.build_memory_circuit(number_of_rounds=11, logic_check="Z")
-    dem = code.memory_circuit.detector_error_model(decompose_errors=True)
-    s = dem.summary()
+    # SURVEY 8d sizes are those of the symptom-merged (= undecomposed) model ...
+    s = code.memory_circuit.detector_error_model().summary()
     assert (s["D"], s["O"], s["M"], s["nnz_H"], s["nnz_L"]) == (1320, 1, 24483, 79956, 835), s
     assert abs(s["sum_p"] - 36.94) < 0.005 and abs(s["min_p"] - 3.341e-4) < 1e-7 and abs(s["max_p"] - 2.2227e-2) < 1e-6
+    # ... the model sinter asks Stim for is the decomposed one, where every distinct decomposition of a symptom is an
+    # error of its own (graphqec_b200/dem.py): same symptoms, same total rates, 27 680 lines
+    dem = code.memory_circuit.detector_error_model(decompose_errors=True)
+    s = dem.summary()
+    assert (s["D"], s["O"], s["M"], s["nnz_H"], s["nnz_L"]) == (1320, 1, 27680, 92594, 871), s
+    assert abs(s["sum_p"] - 36.942) < 0.005
     return dem
 
 

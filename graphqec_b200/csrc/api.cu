@@ -1,5 +1,6 @@
 // Decoder handle, host-buffer entry point (sinter's decode_shots_bit_packed) and the fused
 // sample -> decode -> count pipeline (one sinter worker batch).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -35,6 +36,16 @@ __global__ void sm_to_b8_kernel(const uint32_t *src, uint32_t OW, uint32_t row_b
 #ifndef GQ_COLLECT_CHUNK_LOG2
 #define GQ_COLLECT_CHUNK_LOG2 22   // = matching.cu's decode slice: per-slice launch overheads and tails amortise over 4M shots
 #endif
+
+// timing events of one call, destroyed on every exit path
+struct EventSet {
+    cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~EventSet() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    cudaError_t make(int n) {
+        for (int i = 0; i < n; ++i) { cudaError_t rc = cudaEventCreate(&e[i]); if (rc != cudaSuccess) return rc; }
+        return cudaSuccess;
+    }
+};
 
 static void default_params(gq_decoder_params *p) {
     memset(p, 0, sizeof(*p));
@@ -164,22 +175,27 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
     // Software pipeline over chunks: the H2D copy of chunk c+1 runs on a second stream while chunk c is
     // decoded (the decoder synchronises its own stream with the host; the copy stream keeps going).
     // Two raw-input buffers; a buffer is free again once its rows were re-strided into d_dets.
-    // Chunk schedule: 2^18, 2^19, 2^20, then 2^21 shots -- a short first chunk keeps the one copy that cannot
-    // overlap anything short, each later copy hides behind the decode of the chunk before it (the decoder is
-    // ~4x slower than PCIe), and the big chunks amortise the decoder's per-slice launch overheads and tails.
-    // A remainder shorter than 2^19 shots rides with the chunk before it.
+    // Chunk schedule: 2^F, 2^(F+1), ... doubling up to 2^X shots, then 2^X each (F = 16, X = 19 by default;
+    // GQ_B8_FIRST_LOG2 / GQ_B8_MAX_LOG2 in the environment override).  The first copy is the only one that cannot
+    // overlap anything, so it is short; every later copy hides behind the decode of the chunk before it as long as
+    // PCIe delivers the 165 B/shot faster than the decoder consumes them at half the chunk size -- with equal-size
+    // chunks from 2^X on that holds down to ~12 GB/s per GPU, which is what eight ranks sharing one host's memory
+    // see; the doubling schedule of round 1 (up to 2^21) exposed 4.5 ms per call there.
+    // A remainder shorter than half a chunk rides with the chunk before it.
     std::vector<uint64_t> cstart;
     uint64_t chunk = 0;
     {
-        uint64_t at = 0, sz = nshots >= (1ull << 21) ? (1ull << 18) : (nshots > (1ull << 19) ? (1ull << 18) : (1ull << 20));
-        const bool grow = nshots >= (1ull << 21);
+        static const int first_log2 = []() { const char *e = getenv("GQ_B8_FIRST_LOG2"); int v = e ? atoi(e) : 16; return std::min(std::max(v, 10), 24); }();
+        static const int max_log2 = []() { const char *e = getenv("GQ_B8_MAX_LOG2"); int v = e ? atoi(e) : 19; return std::min(std::max(v, 10), GQ_COLLECT_CHUNK_LOG2); }();
+        uint64_t at = 0, sz = 1ull << std::min(first_log2, max_log2);
+        const uint64_t cap = 1ull << max_log2;
         while (at < nshots) {
             uint64_t ns = std::min(sz, nshots - at);
-            if (nshots - at - ns < (1ull << 19) && grow) ns = nshots - at;
+            if (nshots - at - ns < sz / 2) ns = nshots - at;
             cstart.push_back(at);
             chunk = std::max(chunk, ns);
             at += ns;
-            if (grow && sz < (1ull << 21)) sz <<= 1;
+            if (sz < cap) sz <<= 1;
         }
         cstart.push_back(nshots);
     }
@@ -191,10 +207,9 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
             GQ_CUDA(cudaEventCreateWithFlags(&dec->ev_consumed[i], cudaEventDisableTiming));
         }
     }
-    cudaEvent_t e0, e1, e2, e3, ea, ez;
-    GQ_CUDA(cudaEventCreate(&e0)); GQ_CUDA(cudaEventCreate(&e1));
-    GQ_CUDA(cudaEventCreate(&e2)); GQ_CUDA(cudaEventCreate(&e3));
-    GQ_CUDA(cudaEventCreate(&ea)); GQ_CUDA(cudaEventCreate(&ez));
+    EventSet evs;
+    GQ_CUDA(evs.make(6));
+    cudaEvent_t e0 = evs.e[0], e1 = evs.e[1], e2 = evs.e[2], e3 = evs.e[3], ea = evs.e[4], ez = evs.e[5];
     double t_wait = 0, t_dec = 0, t_d2h = 0;
     int launches = 0;
     memset(dec->kprof, 0, sizeof(dec->kprof));
@@ -251,8 +266,6 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
     GQ_CUDA(cudaStreamSynchronize(dec->copy_stream));
     float total = 0;
     cudaEventElapsedTime(&total, ea, ez);
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
-    cudaEventDestroy(ea); cudaEventDestroy(ez);
     double *t = dec->timing;
     t[0] = 0; t[1] = t_dec; t[2] = 0; t[3] = total; t[4] = t_wait; t[5] = t_d2h; t[6] = launches; t[7] = 0;
     return GQ_OK;
@@ -269,8 +282,9 @@ extern "C" int gq_collect(gq_dem *dem, gq_dec *dec, uint64_t seed, uint64_t shot
     const uint64_t chunk = 1ull << GQ_COLLECT_CHUNK_LOG2;  // multiple of every tile size
     int rc = ensure_scratch(dec, std::min(chunk, nshots));
     if (rc) return rc;
-    cudaEvent_t ev[4];
-    for (int i = 0; i < 4; ++i) GQ_CUDA(cudaEventCreate(&ev[i]));
+    EventSet evs;
+    GQ_CUDA(evs.make(4));
+    cudaEvent_t *ev = evs.e;
     GQ_CUDA(cudaMemsetAsync(dec->d_count, 0, 8, dem->stream));
     double t_s = 0, t_d = 0, t_c = 0;
     int launches = 0;
@@ -305,7 +319,6 @@ extern "C" int gq_collect(gq_dem *dem, gq_dec *dec, uint64_t seed, uint64_t shot
         cudaEventElapsedTime(&ms, ev[2], ev[3]); t_c += ms;
         if (max_errors && errors >= max_errors) break;
     }
-    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
     out[0] = done; out[1] = errors; out[2] = 0;
     double *t = dec->timing;
     t[0] = t_s; t[1] = t_d; t[2] = t_c; t[3] = t_s + t_d + t_c; t[4] = 0; t[5] = 8; t[6] = launches; t[7] = 0;

@@ -158,59 +158,147 @@ struct Parser {
 
 struct Row { Sym dets; uint64_t obs; double p; };
 
-struct Decomposer {
-    // graphlike symptom (1 or 2 detectors) -> its observable masks, ascending
-    std::map<std::pair<uint32_t, uint32_t>, std::vector<uint64_t>> graphlike;
-    std::vector<std::pair<uint32_t, uint32_t>> acc;
-    std::vector<uint32_t> best_a, best_b;
-    std::vector<uint64_t> best_o;
-    bool have = false;
-    uint64_t omask = 0;
+const uint32_t SEP = 0xFFFFFFFFu;   // component separator inside a decomposed key ("^" in Stim's text)
 
-    void leaf() {
-        // first combination (the first block's choice varies slowest) whose masks XOR to omask
-        const size_t n = acc.size();
-        std::vector<const std::vector<uint64_t> *> ch(n);
-        for (size_t i = 0; i < n; ++i) ch[i] = &graphlike[acc[i]];
-        std::vector<size_t> idx(n, 0);
-        for (;;) {
-            uint64_t x = 0;
-            for (size_t i = 0; i < n; ++i) x ^= (*ch[i])[idx[i]];
-            if (x == omask) {
-                have = true;
-                best_a.clear(); best_b.clear(); best_o.clear();
-                for (size_t i = 0; i < n; ++i) { best_a.push_back(acc[i].first); best_b.push_back(acc[i].second); best_o.push_back((*ch[i])[idx[i]]); }
+inline int sym_ndet(const Sym &s) {
+    int n = 0;
+    for (uint32_t x : s) n += !(x & OBS_BIT);
+    return n;
+}
+
+// decompose_errors = True, restated after Stim's ErrorAnalyzer; the two stages are described in
+// graphqec_b200/dem.py (the readable statement of the same algorithm; tests/test_dem.py keeps the two bit-identical).
+//
+// Stage 1: keys (component lists) of the Pauli products k = 1 .. n - 1 of ONE channel.  sym[k] = symptom of product k.
+// Returns false when the channel touches more than 15 detectors (Stim: "too many detectors to find reducible errors").
+bool in_channel_keys(const Sym *sym, int n, std::vector<Sym> &keys, std::string &err) {
+    keys.assign(n, Sym());
+    int cnt[16], maxc = 0;
+    for (int k = 1; k < n; ++k) { keys[k] = sym[k]; cnt[k] = sym_ndet(sym[k]); maxc = std::max(maxc, cnt[k]); }
+    if (maxc <= 2) return true;
+    Sym involved;
+    for (int k = 1; k < n; ++k) for (uint32_t x : sym[k]) if (!(x & OBS_BIT)) involved.push_back(x);
+    std::sort(involved.begin(), involved.end());
+    involved.erase(std::unique(involved.begin(), involved.end()), involved.end());
+    if (involved.size() > 15) { err = "An error involves too many detectors (>15) to find reducible errors."; return false; }
+    uint32_t dm[16];
+    for (int k = 1; k < n; ++k) {
+        dm[k] = 0;
+        for (uint32_t x : sym[k]) if (!(x & OBS_BIT)) dm[k] |= 1u << (std::lower_bound(involved.begin(), involved.end(), x) - involved.begin());
+    }
+    uint32_t singles = 0;
+    for (int k = 1; k < n; ++k) if (cnt[k] == 1) singles |= dm[k];
+    int irr[16], nirr = 0;
+    for (int k = 1; k < n; ++k) if (cnt[k] == 2 && (dm[k] & ~singles)) irr[nirr++] = k;
+    Sym acc, tmp;
+    for (int g = 1; g < n; ++g) {
+        if (cnt[g] <= 2) continue;
+        const uint32_t goal = dm[g];
+        int parts[16], np = 0;
+        uint32_t rem = goal;
+        if (goal & ~singles) {
+            bool found = false;
+            for (int i = 0; i < nirr && !found; ++i) {
+                const uint32_t mk = dm[irr[i]];
+                if ((goal & mk) == mk && (goal & ~(singles | mk)) == 0) { parts[0] = irr[i]; np = 1; rem = goal & ~mk; found = true; }
+            }
+            for (int i1 = 0; i1 < nirr && !found; ++i1) {
+                const uint32_t m1 = dm[irr[i1]];
+                if ((goal & m1) != m1) continue;
+                for (int i2 = i1 + 1; i2 < nirr && !found; ++i2) {
+                    const uint32_t m2 = dm[irr[i2]];
+                    if ((m1 & m2) == 0 && (goal & m2) == m2 && (goal & ~(singles | m1 | m2)) == 0) {
+                        parts[0] = irr[i1]; parts[1] = irr[i2]; np = 2; rem = goal & ~(m1 | m2); found = true;
+                    }
+                }
+            }
+            if (!found) continue;
+        }
+        for (int k = 1; k < n && rem; ++k)
+            if (cnt[k] == 1 && (dm[k] & ~rem) == 0) { rem &= ~dm[k]; parts[np++] = k; }
+        if (rem) continue;
+        acc.clear();
+        for (int i = 0; i < np; ++i) sym_xor(acc, sym[parts[i]], tmp);
+        if (acc != sym[g]) continue;   // the pieces must reproduce the observables too, else stage 2 deals with it
+        Sym &key = keys[g];
+        key.clear();
+        for (int i = 0; i < np; ++i) {
+            if (i) key.push_back(SEP);
+            key.insert(key.end(), sym[parts[i]].begin(), sym[parts[i]].end());
+        }
+    }
+    return true;
+}
+
+struct Entry { Sym key; double p; };
+
+// Stage 2: greedy global pass over all errors in Stim order (plain lexicographic order of the keys: detector ids <
+// OBS_BIT | observable < SEP); errors that end up with the same decomposition merge.  false = decomposition failure.
+bool global_decomposition_pass(std::vector<Entry> &entries, std::string &err) {
+    std::sort(entries.begin(), entries.end(), [](const Entry &a, const Entry &b) { return a.key < b.key; });
+    std::map<std::pair<uint32_t, uint32_t>, Sym> known;   // detectors of a graphlike component -> the first such component
+    auto each_component = [](const Sym &key, auto &&fn) {
+        size_t b = 0;
+        for (size_t i = 0; i <= key.size(); ++i)
+            if (i == key.size() || key[i] == SEP) { fn(key.data() + b, key.data() + i); b = i + 1; }
+    };
+    for (const Entry &e : entries)
+        each_component(e.key, [&](const uint32_t *b, const uint32_t *en) {
+            uint32_t d[3]; int nd = 0;
+            for (const uint32_t *q = b; q < en; ++q) if (!(*q & OBS_BIT)) { if (nd < 3) d[nd] = *q; ++nd; }
+            if (nd == 1 || nd == 2) known.emplace(std::make_pair(d[0], nd == 2 ? d[1] : GQ_NO_DET), Sym(b, en));
+        });
+    std::vector<Entry> out;
+    std::unordered_map<Sym, uint32_t, SymHash> index;
+    Sym left, tmp, dets;
+    for (const Entry &e : entries) {
+        Sym nk;
+        bool ok = true;
+        auto push = [&](const Sym &c) { if (!nk.empty()) nk.push_back(SEP); nk.insert(nk.end(), c.begin(), c.end()); };
+        each_component(e.key, [&](const uint32_t *b, const uint32_t *en) {
+            if (!ok) return;
+            dets.clear();
+            for (const uint32_t *q = b; q < en; ++q) if (!(*q & OBS_BIT)) dets.push_back(*q);
+            if (dets.size() <= 2) { push(Sym(b, en)); return; }
+            std::vector<char> done(dets.size(), 0);
+            left.assign(b, en);
+            for (size_t i = 0; i < dets.size(); ++i) {
+                if (done[i]) continue;
+                for (size_t j = i + 1; j < dets.size(); ++j) {
+                    if (done[j]) continue;
+                    auto it = known.find(std::make_pair(dets[i], dets[j]));
+                    if (it != known.end()) { done[i] = done[j] = 1; push(it->second); sym_xor(left, it->second, tmp); break; }
+                }
+            }
+            int missed = 0;
+            for (size_t i = 0; i < dets.size(); ++i) {
+                if (done[i]) continue;
+                auto it = known.find(std::make_pair(dets[i], GQ_NO_DET));
+                if (it != known.end()) { done[i] = 1; push(it->second); sym_xor(left, it->second, tmp); }
+                else ++missed;
+            }
+            if (missed > 2 || (!left.empty() && sym_ndet(left) == 0)) {
+                err = "Failed to decompose errors into graphlike components with at most two symptoms. The error component that failed to decompose is '";
+                bool first = true;
+                for (const uint32_t *q = b; q < en; ++q) {
+                    if (!first) err += ", ";
+                    first = false;
+                    err += (*q & OBS_BIT) ? "L" + std::to_string(*q & 63) : "D" + std::to_string(*q);
+                }
+                err += "'.";
+                ok = false;
                 return;
             }
-            size_t k = n;
-            while (k > 0) { --k; if (++idx[k] < ch[k]->size()) break; idx[k] = 0; if (k == 0) return; }
-            if (n == 0) return;
-        }
+            if (!left.empty()) push(left);   // remnant edge
+        });
+        if (!ok) return false;
+        auto it = index.find(nk);
+        if (it == index.end()) { index.emplace(nk, (uint32_t)out.size()); out.push_back(Entry{nk, e.p}); }
+        else { double &old = out[it->second].p; old = old * (1.0 - e.p) + e.p * (1.0 - old); }
     }
-    void rec(const Sym &rest) {
-        if (have && acc.size() >= best_a.size()) return;
-        if (rest.empty()) { leaf(); return; }
-        const uint32_t a = rest[0];
-        for (size_t j = 1; j < rest.size(); ++j) {
-            std::pair<uint32_t, uint32_t> blk(a, rest[j]);
-            if (graphlike.count(blk)) {
-                Sym nxt;
-                nxt.reserve(rest.size() - 2);
-                for (size_t k = 1; k < rest.size(); ++k) if (k != j) nxt.push_back(rest[k]);
-                acc.push_back(blk);
-                rec(nxt);
-                acc.pop_back();
-            }
-        }
-        std::pair<uint32_t, uint32_t> single(a, GQ_NO_DET);
-        if (graphlike.count(single)) {
-            Sym nxt(rest.begin() + 1, rest.end());
-            acc.push_back(single);
-            rec(nxt);
-            acc.pop_back();
-        }
-    }
-};
+    entries.swap(out);
+    return true;
+}
 
 }  // namespace
 
@@ -297,6 +385,27 @@ extern "C" int gq_circuit_to_dem(const char *stim_text, int decompose_errors, gq
             old = old * (1.0 - pr) + pr * (1.0 - old);
         }
     };
+    // one noise channel instance: s basis Paulis -> 2^s - 1 products, each an independent error of probability pr
+    Sym csym[16];
+    std::vector<Sym> ckeys;
+    std::string cerr;
+    bool channel_failed = false;
+    auto channel = [&](const Sym *const *basis, int s, double pr) {
+        if (pr <= 0.0 || channel_failed) return;
+        const int n = 1 << s;
+        for (int k = 1; k < n; ++k) {
+            const int low = k & -k, b = __builtin_ctz((unsigned)k);
+            csym[k] = csym[k ^ low];
+            sym_xor(csym[k], *basis[b], tmp);
+        }
+        if (!decompose_errors) {
+            for (int k = 1; k < n; ++k) emit(csym[k], pr);
+            return;
+        }
+        if (!in_channel_keys(csym, n, ckeys, cerr)) { channel_failed = true; return; }
+        for (int k = 1; k < n; ++k) if (!csym[k].empty()) emit(ckeys[k], pr);
+    };
+    csym[0].clear();
     uint32_t m = nmeas;
     for (size_t oi = P.ops.size(); oi-- > 0;) {
         const Op &op = P.ops[oi];
@@ -308,17 +417,19 @@ extern "C" int gq_circuit_to_dem(const char *stim_text, int decompose_errors, gq
             const double q1 = 0.5 - 0.5 * sqrt(1.0 - 4.0 * pr / 3.0);
             for (uint32_t k = op.t0; k < op.t1; ++k) {
                 const uint32_t q = (uint32_t)t[k];
-                emit(xs[q], q1);
-                emit(zs[q], q1);
-                acc2 = xs[q]; sym_xor(acc2, zs[q], tmp);
-                emit(acc2, q1);
+                const Sym *basis[2] = {&xs[q], &zs[q]};
+                channel(basis, 2, q1);
             }
             break;
         }
-        case G_XERR: for (uint32_t k = op.t0; k < op.t1; ++k) emit(xs[t[k]], op.has_arg ? op.arg : 0.0); break;
-        case G_ZERR: for (uint32_t k = op.t0; k < op.t1; ++k) emit(zs[t[k]], op.has_arg ? op.arg : 0.0); break;
+        case G_XERR: for (uint32_t k = op.t0; k < op.t1; ++k) { const Sym *basis[1] = {&xs[t[k]]}; channel(basis, 1, op.has_arg ? op.arg : 0.0); } break;
+        case G_ZERR: for (uint32_t k = op.t0; k < op.t1; ++k) { const Sym *basis[1] = {&zs[t[k]]}; channel(basis, 1, op.has_arg ? op.arg : 0.0); } break;
         case G_YERR:
-            for (uint32_t k = op.t0; k < op.t1; ++k) { acc2 = xs[t[k]]; sym_xor(acc2, zs[t[k]], tmp); emit(acc2, op.has_arg ? op.arg : 0.0); }
+            for (uint32_t k = op.t0; k < op.t1; ++k) {
+                acc2 = xs[t[k]]; sym_xor(acc2, zs[t[k]], tmp);
+                const Sym *basis[1] = {&acc2};
+                channel(basis, 1, op.has_arg ? op.arg : 0.0);
+            }
             break;
         case G_DEP2: {
             const double pr = op.has_arg ? op.arg : 0.0;
@@ -326,11 +437,7 @@ extern "C" int gq_circuit_to_dem(const char *stim_text, int decompose_errors, gq
             const double q2 = 0.5 - 0.5 * pow(1.0 - 16.0 * pr / 15.0, 0.125);
             for (uint32_t k = op.t0; k < op.t1; k += 2) {
                 const Sym *basis[4] = {&xs[t[k]], &zs[t[k]], &xs[t[k + 1]], &zs[t[k + 1]]};
-                for (int sel = 1; sel < 16; ++sel) {
-                    acc2.clear();
-                    for (int b = 0; b < 4; ++b) if (sel & (1 << b)) sym_xor(acc2, *basis[b], tmp);
-                    emit(acc2, q2);
-                }
+                channel(basis, 4, q2);
             }
             break;
         }
@@ -338,7 +445,7 @@ extern "C" int gq_circuit_to_dem(const char *stim_text, int decompose_errors, gq
             for (uint32_t k = op.t1; k-- > op.t0;) {
                 --m;
                 sym_xor(op.gate == G_M ? xs[t[k]] : zs[t[k]], mmask[m], tmp);
-                emit(mmask[m], op.has_arg ? op.arg : 0.0);
+                { const Sym *basis[1] = {&mmask[m]}; channel(basis, 1, op.has_arg ? op.arg : 0.0); }
             }
             break;
         case G_MR: case G_MRX:
@@ -346,7 +453,7 @@ extern "C" int gq_circuit_to_dem(const char *stim_text, int decompose_errors, gq
                 --m;
                 if (op.gate == G_MR) { xs[t[k]] = mmask[m]; zs[t[k]].clear(); }
                 else { zs[t[k]] = mmask[m]; xs[t[k]].clear(); }
-                emit(mmask[m], op.has_arg ? op.arg : 0.0);
+                { const Sym *basis[1] = {&mmask[m]}; channel(basis, 1, op.has_arg ? op.arg : 0.0); }
             }
             break;
         case G_R: case G_RX: for (uint32_t k = op.t0; k < op.t1; ++k) { xs[t[k]].clear(); zs[t[k]].clear(); } break;
@@ -366,54 +473,64 @@ extern "C" int gq_circuit_to_dem(const char *stim_text, int decompose_errors, gq
     }
     if (m != 0) GQ_FAIL(GQ_E_INTERNAL, "measurement bookkeeping out of sync");
 
-    // ---- rows sorted by (detector tuple, observable mask)
-    std::vector<Row> rows(probs.size());
-    for (size_t i = 0; i < probs.size(); ++i) {
-        Row &r = rows[i];
-        r.p = probs[i]; r.obs = 0;
-        for (uint32_t id : *keys[i]) {
-            if (id & OBS_BIT) r.obs |= 1ull << (id & 63);
-            else r.dets.push_back(id);
-        }
-    }
-    std::sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.dets != b.dets ? a.dets < b.dets : a.obs < b.obs; });
-
+    if (channel_failed) GQ_FAIL(GQ_E_UNSUPPORTED, cerr);
     gq_dem_build *B = new gq_dem_build();
     B->D = ndet; B->O = nobs;
     B->det_indptr.push_back(0); B->obs_indptr.push_back(0); B->comp_indptr.push_back(0);
-    for (const Row &r : rows) {
-        B->p.push_back(r.p);
-        B->det_idx.insert(B->det_idx.end(), r.dets.begin(), r.dets.end());
-        B->det_indptr.push_back((uint32_t)B->det_idx.size());
-        for (int k = 0; k < 64; ++k) if ((r.obs >> k) & 1) B->obs_idx.push_back((uint32_t)k);
-        B->obs_indptr.push_back((uint32_t)B->obs_idx.size());
-    }
     B->decomposed = decompose_errors != 0;
-    if (decompose_errors) {
-        Decomposer dc;
-        for (const Row &r : rows)
-            if (r.dets.size() == 1 || r.dets.size() == 2)
-                dc.graphlike[std::make_pair(r.dets[0], r.dets.size() == 2 ? r.dets[1] : GQ_NO_DET)].push_back(r.obs);   // rows are sorted: masks ascend
+    auto push_row = [&](const Sym &whole, double pr) {
+        B->p.push_back(pr);
+        for (uint32_t id : whole) {
+            if (id & OBS_BIT) B->obs_idx.push_back(id & 63);
+            else B->det_idx.push_back(id);
+        }
+        B->det_indptr.push_back((uint32_t)B->det_idx.size());
+        B->obs_indptr.push_back((uint32_t)B->obs_idx.size());
+    };
+    if (!decompose_errors) {
+        // ---- rows sorted by (detector tuple, observable mask)
+        std::vector<Row> rows(probs.size());
+        for (size_t i = 0; i < probs.size(); ++i) {
+            Row &r = rows[i];
+            r.p = probs[i]; r.obs = 0;
+            for (uint32_t id : *keys[i]) {
+                if (id & OBS_BIT) r.obs |= 1ull << (id & 63);
+                else r.dets.push_back(id);
+            }
+        }
+        std::sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.dets != b.dets ? a.dets < b.dets : a.obs < b.obs; });
         for (const Row &r : rows) {
-            if (r.dets.size() <= 2) {
-                B->comp_a.push_back(r.dets.size() >= 1 ? r.dets[0] : GQ_NO_DET);
-                B->comp_b.push_back(r.dets.size() == 2 ? r.dets[1] : GQ_NO_DET);
-                B->comp_obs.push_back(r.obs);
-            } else {
-                dc.have = false; dc.omask = r.obs; dc.acc.clear();
-                dc.rec(r.dets);
-                if (!dc.have) {
-                    std::string msg = "Failed to decompose an error into graphlike components:";
-                    for (uint32_t d : r.dets) msg += " D" + std::to_string(d);
-                    for (int k = 0; k < 64; ++k) if ((r.obs >> k) & 1) msg += " L" + std::to_string(k);
-                    delete B;
-                    GQ_FAIL(GQ_E_UNSUPPORTED, msg);
+            Sym whole(r.dets);
+            for (int k = 0; k < 64; ++k) if ((r.obs >> k) & 1) whole.push_back(OBS_BIT | (uint32_t)k);
+            push_row(whole, r.p);
+        }
+    } else {
+        // ---- Stim's second stage, then one row per distinct decomposition, in Stim's order
+        std::vector<Entry> entries(probs.size());
+        for (size_t i = 0; i < probs.size(); ++i) { entries[i].key = *keys[i]; entries[i].p = probs[i]; }
+        std::string derr;
+        if (!global_decomposition_pass(entries, derr)) { delete B; GQ_FAIL(GQ_E_UNSUPPORTED, derr); }
+        std::sort(entries.begin(), entries.end(), [](const Entry &a, const Entry &b) { return a.key < b.key; });
+        Sym whole, comp;
+        for (const Entry &e : entries) {
+            whole.clear();
+            size_t b0 = 0;
+            for (size_t i = 0; i <= e.key.size(); ++i) {
+                if (i < e.key.size() && e.key[i] != SEP) continue;
+                comp.assign(e.key.begin() + b0, e.key.begin() + i);
+                b0 = i + 1;
+                sym_xor(whole, comp, tmp);
+                uint32_t d[2] = {GQ_NO_DET, GQ_NO_DET};
+                int nd = 0;
+                uint64_t om = 0;
+                for (uint32_t id : comp) {
+                    if (id & OBS_BIT) om |= 1ull << (id & 63);
+                    else if (nd < 2) d[nd++] = id;
                 }
-                B->comp_a.insert(B->comp_a.end(), dc.best_a.begin(), dc.best_a.end());
-                B->comp_b.insert(B->comp_b.end(), dc.best_b.begin(), dc.best_b.end());
-                B->comp_obs.insert(B->comp_obs.end(), dc.best_o.begin(), dc.best_o.end());
+                B->comp_a.push_back(d[0]); B->comp_b.push_back(d[1]); B->comp_obs.push_back(om);
             }
             B->comp_indptr.push_back((uint32_t)B->comp_a.size());
+            push_row(whole, e.p);
         }
     }
     *out = B;

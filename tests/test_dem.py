@@ -76,12 +76,18 @@ def test_steane_dem_sizes():
 
 
 def test_decomposition_surface_code_splits_cleanly():
+    """Stim-style decomposition (dem.py): every piece is graphlike, the pieces XOR to the symptom, every distinct
+    decomposition is its own error, and the symptom-merged probabilities equal the undecomposed model's."""
     code = RotatedSurfaceCode(distance=5, depolarize1_rate=0.005, depolarize2_rate=0.005)
     code.build_memory_circuit(number_of_rounds=5, logic_check="Z")
     dem = code.memory_circuit.detector_error_model(decompose_errors=True)
+    plain = _as_table(code.memory_circuit.detector_error_model())
+    merged, seen = {}, set()
     for i in range(dem.num_errors):
         p, dets, obs = dem.mechanism(i)
         pieces = dem.mechanism_components(i)
+        assert tuple(pieces) not in seen
+        seen.add(tuple(pieces))
         x, om = set(), 0
         for a, b, o in pieces:
             assert a != NO_DET
@@ -91,21 +97,76 @@ def test_decomposition_surface_code_splits_cleanly():
             om ^= o
         assert sorted(x) == list(dets)
         assert om == sum(1 << k for k in obs)
-        assert len(pieces) == (1 if len(dets) <= 2 else 2)
+        assert (len(pieces) == 1) == (len(dets) <= 2)
+        merged[(dets, obs)] = merged.get((dets, obs), 0.0) * (1 - p) + p * (1 - merged.get((dets, obs), 0.0))
+    assert merged.keys() == plain.keys()
+    assert max(abs(merged[k] - plain[k]) for k in plain) < 1e-15
+    # the same symptom reached through different decompositions (Stim keys errors by decomposition): 1910 vs 1677
+    assert dem.num_errors == 1910 and len(plain) == 1677
+
+
+def test_in_channel_stage_prefers_single_detector_pieces():
+    """Stage 1 of Stim's decomposition: when the single-detector errors of a channel cover a composite error of the
+    same channel, they are its decomposition -- not a two-detector edge that happens to exist elsewhere."""
+    from graphqec_b200.dem import _combos, _in_channel_keys
+    nd = 8
+    X_a, Z_a, X_b, Z_b = 0b0001, 0b0110, 0b1000, 0
+    sym = _combos((X_a, Z_a, X_b, Z_b))
+    keys = _in_channel_keys(sym, (1 << nd) - 1)
+    assert keys[0b0111] == (Z_a, X_a, X_b)      # D1 D2 ^ D0 ^ D3: the irreducible pair first, then the singles by channel index
+    assert keys[0b0101] == (X_a ^ X_b,)         # two detectors: graphlike as it is
+    # a basis error that is itself a hyperedge stays whole for the global pass
+    sym = _combos((0b0111, 0b1000))
+    assert _in_channel_keys(sym, 255)[1] == (0b0111,) and _in_channel_keys(sym, 255)[3] == (0b1111,)
+
+
+def test_global_pass_greedy_pairs_remnants_and_failures():
+    from graphqec_b200.dem import _global_decomposition_pass
+    nd = 10
+    L0 = 1 << nd
+    base = {(0b0011,): 0.1, (0b1100 | L0,): 0.2, (0b10000,): 0.05}
+    # known pairs, observables reproduced: D0 D1 ^ D2 D3 L0
+    out = _global_decomposition_pass({**base, **{(0b1111 | L0,): 0.01}}, nd)
+    assert out[(0b0011, 0b1100 | L0)] == 0.01
+    # D0 D1 known, D5 D6 not: remnant edge D5 D6
+    out = _global_decomposition_pass({**base, **{(0b1100011,): 0.03}}, nd)
+    assert out[(0b0011, 0b1100000)] == 0.03
+    # D0 D1 ^ D2 D3 L0 ^ D4 reproduces the detectors but leaves L0 over with no detector to carry it: failure
+    with pytest.raises(ValueError, match="D0, D1, D2, D3, D4"):
+        _global_decomposition_pass({**base, **{(0b11111,): 0.02}}, nd)
+    # three detectors none of which is part of a known piece: failure
+    with pytest.raises(ValueError, match="D5, D6, D7"):
+        _global_decomposition_pass({**base, **{(0b11100000,): 0.04}}, nd)
+    # two errors that end up with the same decomposition merge
+    out = _global_decomposition_pass({**base, **{(0b1111 | L0,): 0.01, (0b0011, 0b1100 | L0): 0.5}}, nd)
+    assert abs(out[(0b0011, 0b1100 | L0)] - (0.01 * 0.5 + 0.5 * 0.99)) < 1e-15
 
 
 def test_decomposition_failure_raises_like_stim():
+    """Steane through CssCode: Hx = Hz gives edges that exist with and without the observable, the greedy pass
+    cannot reproduce the observables from known pieces and the model falls back to the undecomposed one -- which is
+    what reproduces the reference's recorded Steane error rates (tests/test_gpu_reference_stats.py)."""
     H = np.array([[1, 1, 1, 1, 0, 0, 0], [0, 1, 1, 0, 1, 1, 0], [0, 0, 1, 1, 0, 1, 1]])
     st = CssCode(Hx=H, Hz=H, depolarize1_rate=0.005, depolarize2_rate=0.005)
     st.build_memory_circuit(number_of_rounds=3)
-    try:
+    with pytest.raises(ValueError, match="Failed to decompose errors into graphlike components"):
         st.memory_circuit.detector_error_model(decompose_errors=True)
-        decomposed = True
-    except ValueError:
-        decomposed = False
-    # either outcome is legal; the fallback model must always exist
     assert st.memory_circuit.detector_error_model().num_errors == 276
-    assert decomposed in (True, False)
+
+
+def test_toric_through_csscode_decomposes():
+    """BASELINE configs[2]: the hook errors of the serial CssCode schedule (up to 6 detectors) decompose."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_reference_circuits import toric_checks
+    hx, hz = toric_checks(4, 4)
+    tc = CssCode(Hx=hx, Hz=hz, name="Toric", depolarize1_rate=0.006, depolarize2_rate=0.006)
+    tc.build_memory_circuit(number_of_rounds=tc.distance)
+    dem = tc.memory_circuit.detector_error_model(decompose_errors=True)
+    assert dem.decomposed and dem.num_errors == 2832
+    assert tc.memory_circuit.detector_error_model().num_errors == 2368
+    a, b, om, pp = dem.graphlike_components()
+    assert len(a) == dem.comp_a.shape[0]          # every piece is graphlike
 
 
 def test_p_zero_gives_empty_dem():
