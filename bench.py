@@ -34,11 +34,18 @@ SEED = 20261019
 WORKLOAD = "RotatedSurfaceCode d=11 r=11 p=0.005 Z-memory (BASELINE configs[1], north-star point)"
 ALG_BYTES_PER_SHOT = (1320 + 1) / 8.0   # bit-packed syndrome + observable per shot
 # from the committed ncu --set full capture of the dominant kernel (profiles/, this round); None = not captured
-# profiles/r01_tree_solve_kernel3_v8_summary.txt: 465.4 MB read + 7.1 MB written / 767 034 shots (the hand-off
-# records are ~6 B per defect + 16 B of that), 3.446e9 warp-instructions, 69.5 % of issue slots active
-NCU_DRAM_BYTES_PER_SHOT = (465.435904e6 + 7.081728e6) / 767034
-NCU_WARP_INSTR_PER_SHOT = 3446326842 / 767034
-NCU_ISSUE_ACTIVE_PCT = 69.5
+# profiles/r02_tree_solve_kernel3_v1_summary.txt: 464.9 MB read + 7.5 MB written / 767 034 shots (the hand-off
+# records are ~6 B per defect + 16 B of that), 3.465e9 warp-instructions, 75.2 % of issue slots active
+NCU_DRAM_BYTES_PER_SHOT = (464.897792e6 + 7.536128e6) / 767034
+NCU_WARP_INSTR_PER_SHOT = 3465442451 / 767034
+NCU_ISSUE_ACTIVE_PCT = 75.2
+# both arms print this object verbatim (the driver compares it); run-dependent numbers live under "run"
+CONFIG = {"workload": WORKLOAD, "code": "RotatedSurfaceCode", "distance": 11, "rounds": 11, "p": 0.005, "logic_check": "Z",
+          "decoder": "exact minimum-weight perfect matching"}
+# the reference's own recorded throughput for instances of similar size (sinter + PyMatching, unknown CPU, summed
+# worker seconds): /root/reference/notebooks/toric_code.ipynb:184,191
+NOTEBOOK_NOTE = ("reference notebook, sinter+PyMatching per core: toric L=8 (D=1024, p=0.006) 18.3 k shots/s, "
+                 "toric L=12 (D=3456, p=0.006) 4.3 k shots/s (notebooks/toric_code.ipynb:184,191)")
 
 
 _JSON_FD = None
@@ -149,16 +156,18 @@ def cpu_baseline(dem, seconds_target: float = 15.0, threads: int | None = None):
     n, e = po.collect(dem, seed=2, nshots=shots, nthreads=threads, oracle=orc, chunk=20000)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "shots/s", "cores": threads, "kind": "port",
-            "sample": f"{n} shots of the same DEM: oracle DEM sampler + exact blossom MWPM + count, {threads} threads, {dt:.1f} s; {e} logical errors"}, (n, e, dt)
+            "sample": f"{n} shots of the same DEM: oracle DEM sampler + exact blossom MWPM + count, {threads} threads, {dt:.1f} s; {e} logical errors; "
+                      f"{n / dt / threads:.0f} shots/s per core -- an O(n^3) dense blossom, several times slower per core than the real wheels; {NOTEBOOK_NOTE}"}, (n, e, dt)
 
 
 def run_reference(args):
+    """The reference's path on the host cores.  Its wheels (stim / sinter / pymatching) cannot be installed in this
+    image, so this is the oracle port; the process never loads the product's library: the DEM comes from the
+    pure-Python builder (graphqec_b200/dem.py) and everything timed is oracle/liboracle.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import __graft_entry__ as ge
-
-    ge.build()
+    os.environ["GQEC_PY_DEM"] = "1"
     dem = north_star_dem()
     from oracle import pyoracle as po
 
@@ -185,10 +194,11 @@ def run_reference(args):
         "impl": "reference", "metric": "decoded shots/sec", "value": val, "unit": "shots/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "shots_per_step": per_step, "logical_errors": errors},
+        "config": dict(CONFIG),
+        "run": {"shots_per_step": per_step, "logical_errors": errors, "logical_error_rate": errors / max(1, shots)},
         "cpu_baseline": {"value": val, "unit": "shots/s", "cores": threads, "kind": "port",
-                         "sample": f"{per_step} shots/step x {args.steps} steps, oracle port (DEM sampler + exact MWPM + count), {threads} threads; "
-                                   "the reference's wheels (stim/sinter/pymatching) are not installable here"},
+                         "sample": f"{per_step} shots/step x {args.steps} steps, oracle port (DEM sampler + exact MWPM + count), {threads} threads, "
+                                   f"{val / threads:.0f} shots/s per core; the reference's wheels (stim/sinter/pymatching) are not installable here; {NOTEBOOK_NOTE}"},
         "e2e": {"value": val, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -329,7 +339,15 @@ def main():
         per_launch_ms = k_ms / max(1, k_launches)
         shots_per_launch = k_shots / max(1, k_launches)
         achieved = ALG_BYTES_PER_SHOT * shots_per_launch / max(per_launch_ms * 1e-3, 1e-12) / 1e9
+        samp_gbs = ALG_BYTES_PER_SHOT * shots / max(samp_ms / max(1, args.steps) * 1e-3, 1e-12) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                # the fraction the metric text names: sampling / extraction (sample_kernel, K1 + K2 fused with the
+                # classification), bit-packed syndrome + observable written once
+                "sampler": {"kernel": "sample_kernel (K1+K2)", "achieved": samp_gbs, "frac": samp_gbs / peak, "unit": "GB/s",
+                            "shots_per_s": shots / max(samp_ms / max(1, args.steps) * 1e-3, 1e-12),
+                            "bound_note": "Philox + log1pf + shared-memory atomicXor issue, not HBM (profiles/r02_sample_kernel_v1_summary.txt)"},
+                "whole_step": {"achieved": ALG_BYTES_PER_SHOT * shots / max(dev_ms / max(1, args.steps) * 1e-3, 1e-12) / 1e9,
+                               "frac": ALG_BYTES_PER_SHOT * shots / max(dev_ms / max(1, args.steps) * 1e-3, 1e-12) / 1e9 / peak},
                 "traffic": NCU_DRAM_BYTES_PER_SHOT * shots_per_launch if NCU_DRAM_BYTES_PER_SHOT else None,
                 "kernel": "tree_solve_kernel<%d> (K3a, blossom phases of the shots with %d..%d defects)" % (k_K, 32 * (k_K - 1) + 1, 32 * k_K),
                 "peak_source": "MEASURED_PEAKS.json (hbm_gbs, burst)" if peaks else "fallback",
@@ -351,11 +369,12 @@ def main():
             "metric": "decoded shots/sec", "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "shots_per_step_per_gpu": shots, "decoder": "exact MWPM (warp-per-shot blossom, per-K kernels)",
-                       "l2": "inputs larger than L2: each step streams %d MB of syndromes per GPU" % (shots * 168 // 2**20),
-                       "logical_errors": tot_err, "logical_error_rate": tot_err / max(1, tot_shots), "ler_wilson95": [lo, hi],
-                       "device_ms_per_step": dev_ms / max(1, args.steps), "sample_ms_per_step": samp_ms / max(1, args.steps),
-                       "decode_ms_per_step": dec_ms / max(1, args.steps)},
+            "config": dict(CONFIG),
+            "run": {"shots_per_step_per_gpu": shots, "kernels": "warp-per-shot blossom, per-K start / solve kernels, dynamic work distribution",
+                    "l2": "inputs larger than L2: each step streams %d MB of syndromes per GPU" % (shots * 168 // 2**20),
+                    "logical_errors": tot_err, "logical_error_rate": tot_err / max(1, tot_shots), "ler_wilson95": [lo, hi],
+                    "device_ms_per_step": dev_ms / max(1, args.steps), "sample_ms_per_step": samp_ms / max(1, args.steps),
+                    "decode_ms_per_step": dec_ms / max(1, args.steps)},
             "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": ne * db, "d2h_bytes_per_step": ne,
                     "api": "gq_decode_b8 (decode_shots_bit_packed layout), pinned host syndromes, host failure count",
                     "shots_per_step": ne, "logical_errors": e2e_err,

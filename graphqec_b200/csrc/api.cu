@@ -8,19 +8,59 @@
 
 #include "gq_common.h"
 
-// sinter's b8 rows (ceil(D/8) bytes, unpadded) -> 4-byte aligned "sm" rows; one thread per output word
-__global__ void b8_to_sm_kernel(const uint8_t *src, uint32_t row_bytes, uint32_t DW, uint64_t nshots, uint32_t *dst) {
-    const uint64_t total = nshots * DW;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t s = i / DW;
-        const uint32_t w = (uint32_t)(i - s * DW);
-        const uint8_t *r = src + s * row_bytes + (size_t)w * 4;
-        const uint32_t left = row_bytes - w * 4;
-        uint32_t v = r[0];
-        if (left > 1) v |= (uint32_t)r[1] << 8;
-        if (left > 2) v |= (uint32_t)r[2] << 16;
-        if (left > 3) v |= (uint32_t)r[3] << 24;
-        dst[i] = v;
+// sinter's b8 rows (ceil(D/8) bytes, unpadded) -> 4-byte aligned "sm" rows.  One warp per row, lanes = words; the same
+// pass counts the row's defects and appends the shot to the matching decoder's per-class list (cls.counts != null),
+// with one global atomic per (block iteration, class) -- what classify_kernel would do in a pass of its own.
+__global__ void __launch_bounds__(256) b8_to_sm_kernel(const uint8_t *src, uint32_t row_bytes, uint32_t DW, uint32_t D, uint64_t nshots,
+                                                       uint32_t *dst, GqClassifyOut cls) {
+    __shared__ uint32_t cl_cnt[16], cl_base[16];
+    __shared__ uint16_t cl_pos[8];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t tail_mask = (D & 31) ? (1u << (D & 31)) - 1u : 0xffffffffu;
+    for (uint64_t s0 = (uint64_t)blockIdx.x * 8; s0 < nshots; s0 += (uint64_t)gridDim.x * 8) {
+        const uint64_t s = s0 + wib;
+        if (cls.counts) {
+            if (threadIdx.x < 16) cl_cnt[threadIdx.x] = 0;
+            __syncthreads();
+        }
+        uint32_t n = 0;
+        if (s < nshots) {
+            const uint8_t *r = src + s * row_bytes;
+            for (uint32_t w = lane; w < DW; w += 32) {
+                const uint32_t left = row_bytes - w * 4;
+                uint32_t v = r[4 * w];
+                if (left > 1) v |= (uint32_t)r[4 * w + 1] << 8;
+                if (left > 2) v |= (uint32_t)r[4 * w + 2] << 16;
+                if (left > 3) v |= (uint32_t)r[4 * w + 3] << 24;
+                if (w == DW - 1) v &= tail_mask;
+                dst[s * DW + w] = v;
+                n += __popc(v);
+            }
+        }
+        if (!cls.counts) continue;
+        n = __reduce_add_sync(0xffffffffu, n);
+        if (lane == 0) {
+            cl_pos[wib] = 0xffffu;
+            if (s < nshots) {
+                if (n == 0) {
+                    for (uint32_t w = 0; w < cls.OW; ++w) cls.pred[s * cls.OW + w] = 0u;
+                } else {
+                    const uint32_t c = (uint32_t)gq_mt_class_of((int)n);
+                    cl_pos[wib] = (uint16_t)((c << 12) | atomicAdd(&cl_cnt[c], 1u));
+                    if (c == (uint32_t)GQ_MT_CLASSES) atomicMax(&cls.overflow[1], n);
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x <= (uint32_t)GQ_MT_CLASSES && cl_cnt[threadIdx.x])
+            cl_base[threadIdx.x] = atomicAdd(threadIdx.x < (uint32_t)GQ_MT_CLASSES ? &cls.counts[threadIdx.x] : &cls.overflow[0], cl_cnt[threadIdx.x]);
+        __syncthreads();
+        if (lane == 0 && cl_pos[wib] != 0xffffu) {
+            const uint32_t c = cl_pos[wib] >> 12, at = cl_base[c] + (cl_pos[wib] & 0xfffu);
+            if (c < (uint32_t)GQ_MT_CLASSES) cls.lists[(size_t)c * cls.list_stride + at] = (uint32_t)s;
+            else if (at < cls.overflow_cap) cls.overflow[2 + at] = (uint32_t)s;
+        }
+        __syncthreads();
     }
 }
 
@@ -241,13 +281,16 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
         if (c + 1 < nchunks) { rc = issue_copy(c + 1); if (rc) return rc; }
         GQ_CUDA(cudaEventRecord(e0, dem->stream));
         GQ_CUDA(cudaStreamWaitEvent(dem->stream, dec->ev_copied[buf], 0));
-        // the b8 rows arrive contiguous; re-stride them to 4-byte aligned rows on the device
-        b8_to_sm_kernel<<<dem->num_sms * 8, 256, 0, dem->stream>>>(d_in[buf], (uint32_t)db, dem->DW, ns, dec->d_dets);
+        // the b8 rows arrive contiguous; re-stride them to 4-byte aligned rows on the device, classifying on the way
+        GqClassifyOut cls;
+        const bool fused_cls = dec->kind == GQ_DECODER_MATCHING && !dec->params.legacy_tiers && ns <= (1ull << GQ_COLLECT_CHUNK_LOG2);
+        if (fused_cls && (rc = gq_matching_classify_targets(dec, dec->d_pred, &cls))) return rc;
+        b8_to_sm_kernel<<<dem->num_sms * 8, 256, 0, dem->stream>>>(d_in[buf], (uint32_t)db, dem->DW, dem->D, ns, dec->d_dets, cls);
         GQ_CUDA(cudaGetLastError());
         ++launches;
         GQ_CUDA(cudaEventRecord(dec->ev_consumed[buf], dem->stream));
         GQ_CUDA(cudaEventRecord(e1, dem->stream));
-        rc = decode_dispatch(dec, dec->d_dets, ns, dec->d_pred, nullptr, nullptr, nullptr, &launches);
+        rc = decode_dispatch(dec, dec->d_dets, ns, dec->d_pred, nullptr, nullptr, nullptr, &launches, fused_cls);
         if (rc) return rc;
         GQ_CUDA(cudaEventRecord(e2, dem->stream));
         sm_to_b8_kernel<<<dem->num_sms * 2, 256, 0, dem->stream>>>(dec->d_pred, dem->OW, (uint32_t)ob, ns, d_out);

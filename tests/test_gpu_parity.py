@@ -41,7 +41,13 @@ def make_dem(kind, p, **kw):
         Hx, Hz = _toric(kw.pop("L"))
         code = gq.CssCode(Hx=Hx, Hz=Hz, name="Toric", depolarize1_rate=p, depolarize2_rate=p)
     else:
+        lc = kw.pop("logic_check", "Z")
         code = getattr(gq, kind)(**kw, depolarize1_rate=p, depolarize2_rate=p)
+        code.build_memory_circuit(number_of_rounds=kw.get("rounds", code.distance), logic_check=lc)
+        try:
+            return code.memory_circuit.detector_error_model(decompose_errors=True)
+        except ValueError:
+            return code.memory_circuit.detector_error_model()
     code.build_memory_circuit(number_of_rounds=kw.get("rounds", code.distance), logic_check="Z")
     try:
         return code.memory_circuit.detector_error_model(decompose_errors=True)
@@ -63,6 +69,9 @@ CASES = {
     "unrot7": ("UnrotatedSurfaceCode", 0.008, {"distance": 7}),      # > 255 defects for some shots: memory tier
     "steane": ("steane", 0.003, {}),
     "toric4": ("toric", 0.004, {"L": 4}),
+    "rot5_X": ("RotatedSurfaceCode", 0.005, {"distance": 5, "logic_check": "X"}),
+    "unrot5_X": ("UnrotatedSurfaceCode", 0.006, {"distance": 5, "logic_check": "X"}),
+    "rot6_even": ("RotatedSurfaceCode", 0.004, {"distance": 6}),
 }
 _cache = {}
 
@@ -88,10 +97,10 @@ def bits_mm(errs, M, nshots):
 
 
 def oracle_for(dem, dech):
-    u, v, w, om, pr = dech.edges()
-    edges = [(int(a), -1 if int(b) == be.NO_DET else int(b), float(q), int(o)) for a, b, q, o in zip(u, v, pr, om)]
-    return po.MwpmOracle(edges=edges, num_detectors=dem.num_detectors, num_observables=dem.num_observables,
-                         int_weights=w.astype(np.int64)), (u, v, w, om, pr)
+    """The exact-MWPM oracle, built from the DEM by the oracle's own graph builder (merged edges, first observable
+    mask, integer weights) -- NOT from the GPU decoder's edge list; the edge arrays are returned for the correction
+    checks only.  test_matching_graph_equals_oracles_own_build compares the two graphs edge by edge."""
+    return po.MwpmOracle(dem), dech.edges()
 
 
 # ------------------------------------------------------------------------------------------ K1 / K2
@@ -178,7 +187,8 @@ def test_detector_rates_match_dem_marginals():
 # ------------------------------------------------------------------------------------------ K3a
 @pytest.mark.parametrize("name,nshots", [("rep3", 3000), ("rep7", 3000), ("rot3", 3000), ("rot5", 3000), ("rot7", 2000),
                                          ("rot11", 1500), ("unrot5", 1500), ("rot4_even", 2000), ("steane", 3000), ("toric4", 1500),
-                                         ("rot9_hi", 1000), ("rot11_hi", 800), ("unrot7", 600)])
+                                         ("rot9_hi", 1000), ("rot11_hi", 800), ("unrot7", 600), ("rot5_X", 1500), ("unrot5_X", 1000),
+                                         ("rot6_even", 1500)])
 def test_matching_is_optimal_and_corrections_reproduce_syndrome(name, nshots):
     dem, demh, dech = case(name)
     orc, (u, v, w, om, pr) = oracle_for(dem, dech)
@@ -211,8 +221,9 @@ def test_matching_is_optimal_and_corrections_reproduce_syndrome(name, nshots):
 
 
 def test_matching_graph_equals_oracles_own_build():
-    """A8 conventions: merged edges, probabilities and integer weights, built independently."""
-    for name in ("rep7", "rot5", "rot11", "steane"):
+    """A8 conventions: merged edges, probabilities and integer weights, built independently -- every case of this file:
+    repetition, rotated (odd and even d, Z and X memory), unrotated (Z and X), toric and Steane through CssCode."""
+    for name in CASES:
         dem, demh, dech = case(name)
         u, v, w, om, pr = dech.edges()
         got = {(int(a), -1 if int(b) == be.NO_DET else int(b)): (float(q), int(o), int(ww)) for a, b, q, o, ww in zip(u, v, pr, om, w)}
