@@ -215,18 +215,21 @@ extern "C" int gq_decode_b8(gq_dec *dec, const uint8_t *dets_b8, uint64_t nshots
     // Software pipeline over chunks: the H2D copy of chunk c+1 runs on a second stream while chunk c is
     // decoded (the decoder synchronises its own stream with the host; the copy stream keeps going).
     // Two raw-input buffers; a buffer is free again once its rows were re-strided into d_dets.
-    // Chunk schedule: 2^F, 2^(F+1), ... doubling up to 2^X shots, then 2^X each (F = 16, X = 19 by default;
+    // Chunk schedule: 2^F, 2^(F+1), ... doubling up to 2^X shots, then 2^X each (F = 18, X = 20 by default;
     // GQ_B8_FIRST_LOG2 / GQ_B8_MAX_LOG2 in the environment override).  The first copy is the only one that cannot
     // overlap anything, so it is short; every later copy hides behind the decode of the chunk before it as long as
-    // PCIe delivers the 165 B/shot faster than the decoder consumes them at half the chunk size -- with equal-size
-    // chunks from 2^X on that holds down to ~12 GB/s per GPU, which is what eight ranks sharing one host's memory
-    // see; the doubling schedule of round 1 (up to 2^21) exposed 4.5 ms per call there.
+    // PCIe delivers a chunk's 165 B/shot before the decoder is through the chunk before it: while the size doubles
+    // that needs twice the decoder's 22 GB/s, from 2^X on only 22 GB/s.  Every chunk costs ~0.5 ms of launches,
+    // kernel tails and host synchronisations, so chunks should not be small either.  Measured on one B200
+    // (scripts/e2e_probe.py, 2^22 shots, ms per call): (16,19) 38.3, (17,20) 35.9, (18,20) 35.5, (18,21) 34.8,
+    // (18,22) 34.7, one chunk 44.2; the doubling up to 2^21 of round 1 exposed 4.5 ms of copies when eight ranks
+    // shared the host's memory bandwidth, hence X = 20.
     // A remainder shorter than half a chunk rides with the chunk before it.
     std::vector<uint64_t> cstart;
     uint64_t chunk = 0;
     {
-        static const int first_log2 = []() { const char *e = getenv("GQ_B8_FIRST_LOG2"); int v = e ? atoi(e) : 16; return std::min(std::max(v, 10), 24); }();
-        static const int max_log2 = []() { const char *e = getenv("GQ_B8_MAX_LOG2"); int v = e ? atoi(e) : 19; return std::min(std::max(v, 10), GQ_COLLECT_CHUNK_LOG2); }();
+        static const int first_log2 = []() { const char *e = getenv("GQ_B8_FIRST_LOG2"); int v = e ? atoi(e) : 18; return std::min(std::max(v, 10), 24); }();
+        static const int max_log2 = []() { const char *e = getenv("GQ_B8_MAX_LOG2"); int v = e ? atoi(e) : 20; return std::min(std::max(v, 10), GQ_COLLECT_CHUNK_LOG2); }();
         uint64_t at = 0, sz = 1ull << std::min(first_log2, max_log2);
         const uint64_t cap = 1ull << max_log2;
         while (at < nshots) {
