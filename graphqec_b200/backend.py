@@ -77,7 +77,7 @@ SIGNATURES = {
     "gq_decoder_get_edges": (c_int, [c_void_p] * 6),
     "gq_decode": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gq_decode_b8": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
-    "gq_decode_dm": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
+    "gq_decode_dm": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]),
     "gq_count_errors": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "gq_collect": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_uint64, c_uint64, POINTER(c_uint64 * 3)]),
     "gq_last_timing": (c_int, [c_void_p, POINTER(c_double * 8)]),
@@ -328,18 +328,23 @@ class DecoderHandle:
         if want_corrections: out.append(corr)
         return out[0] if len(out) == 1 else tuple(out)
 
-    def decode_dm(self, dets_dm, nshots: int):
+    def decode_dm(self, dets_dm, nshots: int, want_corrections: bool = False):
         """Detector-major in (int32[D, ceil(nshots/32)], what ``DemHandle.extract`` returns), prediction out in the
-        same bit-sliced layout (int32[max(O,1), ceil(nshots/32)])."""
+        same bit-sliced layout (int32[max(O,1), ceil(nshots/32)]); with ``want_corrections`` also the corrections,
+        shot-major as ``decode`` returns them."""
         torch = _torch()
         sw = (int(nshots) + 31) // 32
         pred = torch.zeros((max(self.demh.O, 1), sw), dtype=torch.int32, device=dets_dm.device)
+        corr = None
+        if want_corrections:
+            words = (self.graph_info.num_edges + 31) // 32 if self.kind == MATCHING else (self.demh.M + 31) // 32
+            corr = torch.zeros((int(nshots), max(1, words)), dtype=torch.int32, device=dets_dm.device)
         if nshots == 0:
-            return pred
+            return (pred, corr) if want_corrections else pred
         self.demh._pre()
-        _check(load_library().gq_decode_dm(self._h, _dptr(dets_dm), int(nshots), _dptr(pred)), "gq_decode_dm")
+        _check(load_library().gq_decode_dm(self._h, _dptr(dets_dm), int(nshots), _dptr(pred), _dptr(corr)), "gq_decode_dm")
         self.demh.sync()
-        return pred
+        return (pred, corr) if want_corrections else pred
 
     def decode_b8(self, dets_b8: np.ndarray) -> np.ndarray:
         """Host in, host out, sinter's bit-packed layout (== decode_shots_bit_packed)."""

@@ -116,7 +116,7 @@ extern "C" int gq_decoder_create(gq_dem *dem, int kind, const gq_decoder_params 
     else if (kind == GQ_DECODER_BP_MINSUM) rc = gq_bp_create(dec);
     else { delete dec; GQ_FAIL(GQ_E_INVALID, "gq_decoder_create: unknown decoder kind"); }
     if (rc) { gq_decoder_destroy(dec); return rc; }
-    if (cudaMalloc((void **)&dec->d_count, 8) != cudaSuccess) { gq_decoder_destroy(dec); GQ_FAIL(GQ_E_NOMEM, "gq_decoder_create: out of device memory"); }
+    if (cudaMalloc((void **)&dec->d_count, 16) != cudaSuccess) { gq_decoder_destroy(dec); GQ_FAIL(GQ_E_NOMEM, "gq_decoder_create: out of device memory"); }
     *out = dec;
     return GQ_OK;
 }
@@ -179,18 +179,55 @@ extern "C" int gq_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, 
 static int ensure_scratch(gq_dec *dec, uint64_t nshots);
 
 // detector-major in, detector-major out (32 shots per word): what the bit-sliced extractor (gq_extract) produces
-// and SURVEY 8b lists as gq_decode_dm.  Two bit-matrix transposes around gq_decode, in slices of the scratch size.
-extern "C" int gq_decode_dm(gq_dec *dec, const uint32_t *dets_dm, uint64_t nshots, uint32_t *pred_dm) {
+// and SURVEY 8b lists as gq_decode_dm.  Two bit-matrix transposes around the decoder, in slices of 2^20 shots (a
+// multiple of 32, so a slice starts on a word boundary of the detector-major rows) so that the scratch stays bounded.
+__global__ void dm_slice_gather_kernel(const uint32_t *dm, uint32_t nrows, uint64_t SW, uint64_t w0, uint32_t sw, uint32_t *out) {
+    const uint64_t total = (uint64_t)nrows * sw;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / sw, c = i - r * sw;
+        out[i] = dm[r * SW + w0 + c];
+    }
+}
+__global__ void dm_slice_scatter_kernel(const uint32_t *in, uint32_t nrows, uint64_t SW, uint64_t w0, uint32_t sw, uint32_t *dm) {
+    const uint64_t total = (uint64_t)nrows * sw;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / sw, c = i - r * sw;
+        dm[r * SW + w0 + c] = in[i];
+    }
+}
+
+extern "C" int gq_decode_dm(gq_dec *dec, const uint32_t *dets_dm, uint64_t nshots, uint32_t *pred_dm, uint32_t *corr_sm) {
     if (!dec || !dets_dm || !pred_dm) GQ_FAIL(GQ_E_INVALID, "gq_decode_dm: NULL argument");
     if (nshots == 0) return GQ_OK;
     gq_dem *dem = dec->dem;
     GQ_CUDA(cudaSetDevice(dem->device));
-    int rc = ensure_scratch(dec, nshots);
+    const uint64_t slice = 1ull << 20, SW = (nshots + 31) / 32;
+    const uint32_t orows = std::max<uint32_t>(dem->O, 1);
+    const size_t corr_words = dec->kind == GQ_DECODER_MATCHING ? (dec->num_edges + 31) / 32 : (dem->M + 31) / 32;
+    int rc = ensure_scratch(dec, std::min(slice, nshots));
     if (rc) return rc;
-    if ((rc = gq_transpose_dm_to_sm(dem, dets_dm, dem->D, nshots, dec->d_dets))) return rc;
+    // staging for one slice of the detector-major rows (contiguous [rows][slice / 32])
+    const size_t stage_words = (size_t)(dem->D + orows) * (std::min(slice, nshots) + 31) / 32 + 64;
+    uint32_t *stage = nullptr;
+    const bool sliced = nshots > slice;
+    if (sliced) GQ_CUDA(cudaMalloc((void **)&stage, stage_words * 4));
     int launches = 0;
-    if ((rc = decode_dispatch(dec, dec->d_dets, nshots, dec->d_pred, nullptr, nullptr, nullptr, &launches))) return rc;
-    return gq_transpose_sm_to_dm(dem, dec->d_pred, std::max<uint32_t>(dem->O, 1), nshots, pred_dm);
+    for (uint64_t s0 = 0; s0 < nshots && rc == 0; s0 += slice) {
+        const uint64_t ns = std::min(slice, nshots - s0);
+        const uint32_t sw = (uint32_t)((ns + 31) / 32);
+        const uint32_t *src = dets_dm;
+        uint32_t *dst = pred_dm;
+        if (sliced) {
+            dm_slice_gather_kernel<<<dem->num_sms * 4, 256, 0, dem->stream>>>(dets_dm, dem->D, SW, s0 / 32, sw, stage);
+            src = stage; dst = stage + (size_t)dem->D * sw;
+        }
+        if ((rc = gq_transpose_dm_to_sm(dem, src, dem->D, ns, dec->d_dets))) break;
+        if ((rc = decode_dispatch(dec, dec->d_dets, ns, dec->d_pred, nullptr, nullptr, corr_sm ? corr_sm + s0 * corr_words : nullptr, &launches))) break;
+        if ((rc = gq_transpose_sm_to_dm(dem, dec->d_pred, orows, ns, dst))) break;
+        if (sliced) dm_slice_scatter_kernel<<<dem->num_sms, 256, 0, dem->stream>>>(dst, orows, SW, s0 / 32, sw, pred_dm);
+    }
+    if (stage) { cudaStreamSynchronize(dem->stream); cudaFree(stage); }
+    return rc;
 }
 
 static int ensure_scratch(gq_dec *dec, uint64_t nshots) {
@@ -331,11 +368,13 @@ extern "C" int gq_collect(gq_dem *dem, gq_dec *dec, uint64_t seed, uint64_t shot
     EventSet evs;
     GQ_CUDA(evs.make(4));
     cudaEvent_t *ev = evs.e;
-    GQ_CUDA(cudaMemsetAsync(dec->d_count, 0, 8, dem->stream));
+    GQ_CUDA(cudaMemsetAsync(dec->d_count, 0, 16, dem->stream));
+    // BP + OSD marks a shot it could not solve with an all-ones prediction word: sinter's "discards"
+    const uint32_t discard_word = (dec->kind == GQ_DECODER_BP_MINSUM && dec->params.bp_osd && dem->O < 32) ? 0xFFFFFFFFu : 0u;
     double t_s = 0, t_d = 0, t_c = 0;
     int launches = 0;
     memset(dec->kprof, 0, sizeof(dec->kprof));
-    uint64_t done = 0, errors = 0;
+    uint64_t done = 0, errors = 0, counts[2] = {0, 0};
     while (done < nshots) {
         uint64_t ns = std::min(chunk, nshots - done);
         GQ_CUDA(cudaEventRecord(ev[0], dem->stream));
@@ -350,22 +389,23 @@ extern "C" int gq_collect(gq_dem *dem, gq_dec *dec, uint64_t seed, uint64_t shot
         rc = decode_dispatch(dec, dec->d_dets, ns, dec->d_pred, nullptr, nullptr, nullptr, &launches, fused_cls);
         if (rc) return rc;
         GQ_CUDA(cudaEventRecord(ev[2], dem->stream));
-        rc = gq_count_errors(dem, dec->d_pred, dec->d_obs, ns, dec->d_count);
+        rc = gq_count_errors_discards(dem, dec->d_pred, dec->d_obs, ns, discard_word, dec->d_count);
         if (rc) return rc;
         ++launches;
         GQ_CUDA(cudaEventRecord(ev[3], dem->stream));
         done += ns;
         if (max_errors || done >= nshots) {
-            GQ_CUDA(cudaMemcpyAsync(&errors, dec->d_count, 8, cudaMemcpyDeviceToHost, dem->stream));
+            GQ_CUDA(cudaMemcpyAsync(counts, dec->d_count, 16, cudaMemcpyDeviceToHost, dem->stream));
         }
         GQ_CUDA(cudaStreamSynchronize(dem->stream));
+        errors = counts[0];
         float ms;
         cudaEventElapsedTime(&ms, ev[0], ev[1]); t_s += ms;
         cudaEventElapsedTime(&ms, ev[1], ev[2]); t_d += ms;
         cudaEventElapsedTime(&ms, ev[2], ev[3]); t_c += ms;
         if (max_errors && errors >= max_errors) break;
     }
-    out[0] = done; out[1] = errors; out[2] = 0;
+    out[0] = done; out[1] = errors; out[2] = counts[1];
     double *t = dec->timing;
     t[0] = t_s; t[1] = t_d; t[2] = t_c; t[3] = t_s + t_d + t_c; t[4] = 0; t[5] = 8; t[6] = launches; t[7] = 0;
     return GQ_OK;

@@ -1,8 +1,9 @@
 // K3b: batched min-sum belief propagation on the DEM Tanner graph, one shot per thread block.
 //
-// Checks = detectors (D), variables = error mechanisms (M), edges = nnz(H).  Stands in for the BP
-// stage of stimbposd's BP+OSD (reference threshold_lab.py:19,30) -- without OSD,
-// as BASELINE.json's north star asks.  Flooding schedule, fp32 messages:
+// Checks = detectors (D), variables = error mechanisms (M), edges = nnz(H).  Stands in for stimbposd's BP+OSD
+// (reference threshold_lab.py:19,30): min-sum BP as BASELINE.json's north star asks (stimbposd
+// defaults to product-sum), then -- with params.bp_osd -- order-0 OSD (below; stimbposd defaults to OSD-CS(60)).
+// Flooding schedule, fp32 messages:
 //   check c -> variable v :  alpha * (-1)^{s_c} * prod_{v' != v} sign(m_{v'->c}) * min_{v' != v} |m_{v'->c}|
 //   variable v posterior  :  prior_v + sum_c m_{c->v}      (m_{v->c} = posterior - m_{c->v}, formed on the fly)
 // The block keeps one message per edge (check -> variable) and one posterior per variable; they
@@ -22,7 +23,11 @@
 //    independent of the columns already in it (incremental GF(2) elimination on D-bit vectors spread over
 //    the lanes, pivot = lowest set bit, found with a ballot), and the walk stops the moment the syndrome
 //    reduces to zero against the basis -- its representation in a basis is unique, so the later basis
-//    columns of a full OSD-0 would get coefficient 0.  Identical to oracle/bp_oracle.c::orc_osd0.
+//    columns of a full OSD-0 would get coefficient 0.  The basis may grow to D columns (rank(H) <= D), and a
+//    shot whose syndrome the osd_k ordered candidates do not span goes on through every variable in index
+//    order, so every syndrome in the column space of H gets a correction; the (impossible for a DEM's own
+//    shots) rest is counted and reported as sinter's "discards".  Identical to oracle/bp_oracle.c::orc_osd0
+//    with max_candidates = -osd_k.
 #include <math.h>
 #include <string.h>
 
@@ -54,8 +59,10 @@ struct BpArgs {
 };
 
 
-static constexpr int OSD_KMAX = 1024;     // cap on the basis size (one coefficient word per lane)
-static constexpr int OSD_NCAND = 2048;    // candidates kept per shot (BB-144 at p = 3e-3: up to ~1400 are walked, basis <= ~650)
+static constexpr int OSD_NCAND = 2048;    // reliability-ordered candidates kept per shot (BB-144 at p = 3e-3: up to ~1400 are usually walked,
+                                          // basis <= ~650); a shot that needs more goes on through all variables in index order
+// the basis can grow to rank(H) <= D columns: coefficient sets are WPL words per lane like the vectors themselves
+// (32 * 32 * WPL >= D ordinals)
 
 __device__ __forceinline__ uint32_t osd_key(float x) {   // order-preserving map float -> uint32
     const uint32_t b = __float_as_uint(x);
@@ -299,8 +306,11 @@ struct OsdArgs {
     uint32_t nfail;
     uint32_t D, DW, OW, MW, M;
     const uint32_t *var_ptr, *var_chk, *var_obs;
-    uint32_t *scratch;        // per warp: OSD_KMAX x (32 WPL basis words + 32 coefficient words) + OSD_KMAX columns
+    uint32_t *scratch;        // per warp: kmax x (32 WPL basis words + 32 WPL coefficient words) + kmax columns
     size_t scratch_stride;    // words
+    uint32_t kmax;            // basis capacity = D (every independent column fits)
+    uint32_t *giveups;        // shots whose syndrome is not in the column space of H (cannot happen for a DEM's own shots)
+    uint32_t sentinel;        // prediction written for such a shot (0xffffffff: counted as a discard), 0 = leave BP's decision
 };
 
 template <int WPL>
@@ -324,19 +334,20 @@ __global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     uint16_t *piv = piv_all + (size_t)wib * ((a.D + 1) & ~1u);
     uint32_t *basis = a.scratch + (size_t)warp * a.scratch_stride;
-    uint32_t *coef = basis + (size_t)OSD_KMAX * 32 * WPL;
-    uint32_t *col = coef + (size_t)OSD_KMAX * 32;
+    uint32_t *coef = basis + (size_t)a.kmax * 32 * WPL;
+    uint32_t *col = coef + (size_t)a.kmax * 32 * WPL;
     for (uint32_t item = warp; item < a.nfail; item += nwarps) {
         const uint32_t shot = a.fail_list[item];
         const uint32_t *cand = a.cand + (size_t)item * OSD_NCAND;
         for (uint32_t r = lane; r < a.D; r += 32) piv[r] = 0xFFFFu;
-        uint32_t s[WPL], sc = 0;
+        uint32_t s[WPL], sc[WPL];
 #pragma unroll
         for (int j = 0; j < WPL; ++j) {
             const uint32_t w = j * 32 + lane;
             uint32_t word = w < a.DW ? a.dets[(size_t)shot * a.DW + w] : 0u;
             if (w == a.DW - 1 && (a.D & 31)) word &= (1u << (a.D & 31)) - 1u;
             s[j] = word;
+            sc[j] = 0u;
         }
         __syncwarp();
         int nb = 0;
@@ -349,17 +360,18 @@ __global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
                 const uint32_t p = piv[r];
                 if (p == 0xFFFFu) return;
 #pragma unroll
-                for (int j = 0; j < WPL; ++j) s[j] ^= basis[((size_t)p * WPL + j) * 32 + lane];
-                sc ^= coef[(size_t)p * 32 + lane];
+                for (int j = 0; j < WPL; ++j) { s[j] ^= basis[((size_t)p * WPL + j) * 32 + lane]; sc[j] ^= coef[((size_t)p * WPL + j) * 32 + lane]; }
             }
         };
         reduce_s();
-        for (uint32_t i = 0; i < OSD_NCAND && !done && nb < OSD_KMAX; ++i) {
-            const uint32_t c = cand[i];
-            if (c == 0xFFFFFFFFu) break;
-            uint32_t v[WPL], vc = 0;
+        // the reliability-ordered candidates first, then (rare) every variable in index order: the walk ends when the
+        // syndrome is reduced or the basis is complete
+        for (uint32_t i = 0; i < OSD_NCAND + a.M && !done && nb < (int)a.kmax; ++i) {
+            const uint32_t c = i < OSD_NCAND ? cand[i] : i - OSD_NCAND;
+            if (c == 0xFFFFFFFFu) continue;
+            uint32_t v[WPL], vc[WPL];
 #pragma unroll
-            for (int j = 0; j < WPL; ++j) v[j] = 0u;
+            for (int j = 0; j < WPL; ++j) { v[j] = 0u; vc[j] = 0u; }
             for (uint32_t k = a.var_ptr[c]; k < a.var_ptr[c + 1]; ++k) {
                 const uint32_t d = a.var_chk[k], w = d >> 5;
 #pragma unroll
@@ -372,13 +384,14 @@ __global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
                 const uint32_t p = piv[r];
                 if (p != 0xFFFFu) {
 #pragma unroll
-                    for (int j = 0; j < WPL; ++j) v[j] ^= basis[((size_t)p * WPL + j) * 32 + lane];
-                    vc ^= coef[(size_t)p * 32 + lane];
+                    for (int j = 0; j < WPL; ++j) { v[j] ^= basis[((size_t)p * WPL + j) * 32 + lane]; vc[j] ^= coef[((size_t)p * WPL + j) * 32 + lane]; }
                 } else {
-                    if (lane == (nb >> 5)) vc |= 1u << (nb & 31);
 #pragma unroll
-                    for (int j = 0; j < WPL; ++j) basis[((size_t)nb * WPL + j) * 32 + lane] = v[j];
-                    coef[(size_t)nb * 32 + lane] = vc;
+                    for (int j = 0; j < WPL; ++j) {
+                        if ((nb >> 10) == j && lane == ((nb >> 5) & 31)) vc[j] |= 1u << (nb & 31);
+                        basis[((size_t)nb * WPL + j) * 32 + lane] = v[j];
+                        coef[((size_t)nb * WPL + j) * 32 + lane] = vc[j];
+                    }
                     if (lane == 0) { piv[r] = (uint16_t)nb; col[nb] = c; }
                     ++nb;
                     __syncwarp();
@@ -392,19 +405,26 @@ __global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
             uint32_t *corr_row = a.corr_out ? a.corr_out + (size_t)shot * a.MW : nullptr;
             if (corr_row) for (uint32_t w = lane; w < a.MW; w += 32) corr_row[w] = 0u;
             __syncwarp();
-            uint32_t om = 0, bits = sc;
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const uint32_t c = col[32 * lane + b];
-                om ^= a.var_obs[c];
-                if (corr_row) atomicXor(&corr_row[c >> 5], 1u << (c & 31u));
+            uint32_t om = 0;
+#pragma unroll
+            for (int j = 0; j < WPL; ++j) {
+                uint32_t bits = sc[j];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const uint32_t c = col[((j * 32 + lane) << 5) + b];
+                    om ^= a.var_obs[c];
+                    if (corr_row) atomicXor(&corr_row[c >> 5], 1u << (c & 31u));
+                }
             }
             om = __reduce_xor_sync(0xffffffffu, om);
             if (lane == 0) {
                 a.pred[(size_t)shot * a.OW] = om;
                 if (a.flags_out) a.flags_out[shot] = 0;
             }
+        } else if (lane == 0) {
+            atomicAdd(a.giveups, 1u);
+            if (a.sentinel) a.pred[(size_t)shot * a.OW] = a.sentinel;
         }
         __syncwarp();
     }
@@ -500,14 +520,15 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
     const uint64_t chunk = osd ? 16384 : nshots;       // OSD keeps 8 KB of candidates per unconverged shot
     const int wpl = osd_wpl(dem->DW);
     const int osd_blocks = dem->num_sms * 2, osd_warps = osd_blocks * 4;
-    const size_t osd_stride = (size_t)OSD_KMAX * (32 * (size_t)wpl + 32 + 1);
+    const uint32_t osd_kmax = dem->D;
+    const size_t osd_stride = (size_t)osd_kmax * (64 * (size_t)wpl + 1);
     if (osd) {
         if (!dec->d_osd_cand) {
             GQ_CUDA(cudaMalloc((void **)&dec->d_osd_cand, chunk * OSD_NCAND * 4));
-            GQ_CUDA(cudaMalloc((void **)&dec->d_osd_fail, (chunk + 1) * 4));
+            GQ_CUDA(cudaMalloc((void **)&dec->d_osd_fail, (chunk + 2) * 4));   // [0] unconverged count, [1] OSD give-ups, [2..] shots
             GQ_CUDA(cudaMalloc((void **)&dec->d_osd_scratch, (size_t)osd_warps * osd_stride * 4));
         }
-        a.osd_k = OSD_NCAND; a.cand = dec->d_osd_cand; a.fail_list = dec->d_osd_fail + 1; a.fail_count = dec->d_osd_fail;
+        a.osd_k = OSD_NCAND; a.cand = dec->d_osd_cand; a.fail_list = dec->d_osd_fail + 2; a.fail_count = dec->d_osd_fail;
     }
     for (uint64_t s0 = 0; s0 < nshots; s0 += chunk) {
         const uint64_t ns = std::min(chunk, nshots - s0);
@@ -516,7 +537,7 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
         a.flags_out = flags_out ? flags_out + s0 : nullptr;
         a.corr_out = corr_out ? corr_out + s0 * a.MW : nullptr;
         a.nshots = ns;
-        if (osd) GQ_CUDA(cudaMemsetAsync(dec->d_osd_fail, 0, 4, dem->stream));
+        if (osd) GQ_CUDA(cudaMemsetAsync(dec->d_osd_fail, 0, 8, dem->stream));
         int blocks = (int)std::min<uint64_t>(ns, (uint64_t)dec->bp_blocks);
         bp_kernel<<<blocks, 256, smem, dem->stream>>>(a);
         GQ_CUDA(cudaGetLastError());
@@ -530,7 +551,9 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
         OsdArgs o;
         memset(&o, 0, sizeof(o));
         o.dets = a.dets; o.pred = a.pred; o.flags_out = a.flags_out; o.corr_out = a.corr_out;
-        o.cand = dec->d_osd_cand; o.fail_list = dec->d_osd_fail + 1; o.nfail = nfail;
+        o.cand = dec->d_osd_cand; o.fail_list = dec->d_osd_fail + 2; o.nfail = nfail;
+        o.kmax = osd_kmax; o.giveups = dec->d_osd_fail + 1;
+        o.sentinel = dem->O < 32 ? 0xFFFFFFFFu : 0u;
         o.D = dem->D; o.DW = dem->DW; o.OW = dem->OW; o.MW = a.MW; o.M = dem->M;
         o.var_ptr = dec->d_var_ptr; o.var_chk = dec->d_var_chk; o.var_obs = dec->d_var_obs;
         o.scratch = dec->d_osd_scratch; o.scratch_stride = osd_stride;
@@ -544,6 +567,10 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
         }
         GQ_CUDA(cudaGetLastError());
         ++*launches;
+        uint32_t ngive = 0;
+        GQ_CUDA(cudaMemcpyAsync(&ngive, dec->d_osd_fail + 1, 4, cudaMemcpyDeviceToHost, dem->stream));
+        GQ_CUDA(cudaStreamSynchronize(dem->stream));
+        dec->osd_giveups += ngive;
     }
     return GQ_OK;
 }

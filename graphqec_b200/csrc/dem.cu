@@ -237,23 +237,31 @@ __global__ void transpose_sm_to_dm_kernel(const uint32_t *sm, uint32_t nbits, ui
     if (bit < nbits) dm[(size_t)bit * SW + sw] = outw;
 }
 
+// discard_word != 0: a shot whose first prediction word equals it was given up by the decoder (BP+OSD sentinel) -- it is
+// counted in count[1] (sinter's "discards") and not as an error
 __global__ void count_errors_kernel(const uint32_t *pred, const uint32_t *obs, uint64_t nshots,
-                                    uint32_t OW, unsigned long long *count) {
-    uint32_t local = 0;
+                                    uint32_t OW, uint32_t discard_word, unsigned long long *count) {
+    uint32_t local = 0, disc = 0;
     for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nshots;
          s += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t diff = 0;
         for (uint32_t w = 0; w < OW; ++w) diff |= pred[s * OW + w] ^ obs[s * OW + w];
-        local += diff != 0;
+        const bool discarded = discard_word != 0u && pred[s * OW] == discard_word;
+        local += diff != 0 && !discarded;
+        disc += discarded;
     }
     local = __reduce_add_sync(0xffffffffu, local);
-    __shared__ uint32_t part[32];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = local;
+    disc = __reduce_add_sync(0xffffffffu, disc);
+    __shared__ uint32_t part[32], dpart[32];
+    if ((threadIdx.x & 31) == 0) { part[threadIdx.x >> 5] = local; dpart[threadIdx.x >> 5] = disc; }
     __syncthreads();
     if (threadIdx.x < 32) {
         uint32_t v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0;
+        uint32_t d = threadIdx.x < (blockDim.x >> 5) ? dpart[threadIdx.x] : 0;
         v = __reduce_add_sync(0xffffffffu, v);
+        d = __reduce_add_sync(0xffffffffu, d);
         if (threadIdx.x == 0 && v) atomicAdd(count, (unsigned long long)v);
+        if (threadIdx.x == 0 && d) atomicAdd(count + 1, (unsigned long long)d);
     }
 }
 
@@ -529,11 +537,17 @@ extern "C" int gq_transpose_sm_to_dm(gq_dem *dem, const uint32_t *sm, uint32_t n
 
 extern "C" int gq_count_errors(gq_dem *dem, const uint32_t *pred_sm, const uint32_t *obs_sm,
                                uint64_t nshots, uint64_t *count) {
+    return gq_count_errors_discards(dem, pred_sm, obs_sm, nshots, 0u, count);
+}
+
+// count[0] += errors, count[1] += discards (count[1] is only touched when discard_word != 0)
+int gq_count_errors_discards(gq_dem *dem, const uint32_t *pred_sm, const uint32_t *obs_sm, uint64_t nshots,
+                             uint32_t discard_word, uint64_t *count) {
     if (!dem || !pred_sm || !obs_sm || !count) GQ_FAIL(GQ_E_INVALID, "gq_count_errors: NULL argument");
     if (nshots == 0) return GQ_OK;
     GQ_CUDA(cudaSetDevice(dem->device));
     uint32_t grid = (uint32_t)std::min<uint64_t>((nshots + 255) / 256, (uint64_t)dem->num_sms * 8);
-    count_errors_kernel<<<grid, 256, 0, dem->stream>>>(pred_sm, obs_sm, nshots, dem->OW,
+    count_errors_kernel<<<grid, 256, 0, dem->stream>>>(pred_sm, obs_sm, nshots, dem->OW, discard_word,
                                                        (unsigned long long *)count);
     GQ_CUDA(cudaGetLastError());
     return GQ_OK;

@@ -102,6 +102,7 @@ struct gq_dec {
     uint32_t *d_var_chk = nullptr;     // detectors of every variable (columns of H), for OSD
     uint32_t *d_osd_cand = nullptr, *d_osd_fail = nullptr, *d_osd_scratch = nullptr;
     uint64_t osd_shots = 0;            // shots handed to OSD so far
+    uint64_t osd_giveups = 0;          // of those, shots OSD could not solve (syndrome outside the column space of H)
     float *d_bp_msgs = nullptr;
     size_t bp_msgs_per_block = 0;
     int bp_blocks = 0;
@@ -137,6 +138,9 @@ struct GqClassifyOut {
 // dem.cu: gq_sample with the classification fused into the tile flush
 int gq_sample_classified(gq_dem *dem, uint64_t seed, uint64_t shot0, uint64_t nshots, uint32_t *dets_sm,
                          uint32_t *obs_sm, uint32_t *errs_mm, const GqClassifyOut *cls);
+
+int gq_count_errors_discards(gq_dem *dem, const uint32_t *pred_sm, const uint32_t *obs_sm, uint64_t nshots,
+                             uint32_t discard_word, uint64_t *count);
 
 // matching.cu
 int gq_matching_create(gq_dec *dec);

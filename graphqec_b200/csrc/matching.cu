@@ -1,16 +1,18 @@
 // K3a: batched exact matching decoder, one shot per warp.
 //
 // Set-up (host, once per DEM): graphlike pieces of the DEM are merged into the matching graph with
-// PyMatching's conventions (parallel edges merge with p1(1-p2)+p2(1-p1), weight
-// ln((1-p)/p), discretised to integers), then all-pairs shortest paths (one Dijkstra per node, one
-// more from the boundary) give three (D+1)x(D+1) tables resident in HBM/L2: distance (u16),
-// observable mask of that path (u8), and the path's next hop (u16, only if corrections are wanted).
+// PyMatching's conventions (parallel edges merge with p1(1-p2)+p2(1-p1), the first observable
+// mask is kept, weight ln((1-p)/p) discretised to integers), then all-pairs shortest paths (one Dijkstra per
+// node, one more from the boundary) give the tables resident in HBM/L2: distance (u16), observable mask of that
+// path (u8), the path's next hop (u16, only if corrections are wanted) and, per detector, its nearest detectors.
 //
-// Kernel: a warp extracts the defects of its shot from the bit-packed syndrome (ballot/popc
-// compaction), gathers the dense weight matrix W[i][j] = min(d(i,j), b(i)+b(j)) of those defects
-// from the distance table, runs the warp-cooperative blossom solver (blossom_warp.cuh) and XORs the
-// path observables of the matched pairs into the prediction.  Shots with more defects than the
-// fast tier's capacity are queued and solved by a second launch with a larger workspace.
+// First tier (every shot of the surface-code sweeps): the producer of the syndromes (sampler, b8 re-stride kernel,
+// or classify_kernel) sorts the shots of a slice by defect count into per-K lists (K = ceil(defects / 32) slots per
+// lane); per class, tree_start_kernel<K> extracts the defects and computes a tight dual start and
+// tree_solve_kernel<K> runs single-tree primal-dual blossom phases straight on the distance table (match_tree.cuh:
+// no per-shot weight matrix), both claiming shots through an atomic cursor.  Shots with more than 1024 defects, or
+// that the solver gives up on, climb the older dense-matrix ladder (match_fast_kernel<K>: register-resident solver
+// on a gathered weight matrix, blossom_regs.cuh; match_kernel: memory-resident, blossom_warp.cuh).
 #include <math.h>
 #include <string.h>
 

@@ -28,7 +28,8 @@ from graphqec_b200.stats import Task, TaskStats
 __all__ = ["ThresholdLAB"]
 
 # decoder name -> kernel family.  "pymatching" / "fusion_blossom" are exact MWPM in the reference
-# (threshold_lab.py:27-33); "bposd" maps to min-sum BP *without* OSD (BASELINE.json north_star).
+# (threshold_lab.py:27-33); "bposd" (stimbposd.SinterDecoder_BPOSD there: product-sum BP + OSD-CS) maps to the
+# min-sum BP the BASELINE north star names, followed by order-0 OSD on the shots BP leaves unconverged.
 __available_decoders__ = {
     "pymatching": "matching",
     "fusion_blossom": "matching",
@@ -142,7 +143,8 @@ class ThresholdLAB:
         wired up, threshold_lab.py:182-189): a CSV in sinter's schema.  Rows already in it count towards
         ``max_shots`` / ``max_errors`` of the task with the same ``strong_id``; what this call adds is
         appended as one row per task (rank 0 writes).  New shots continue the task's counter-based RNG stream
-        behind the recorded ones (from the next whole tile), so a resumed sweep never re-uses a shot.
+        behind the recorded ones: every row carries the stream position it stopped at (``next_shot`` in sinter's
+        ``custom_counts`` column, a whole number of sampler tiles), so a resumed sweep never re-uses a shot.
         """
         from graphqec_b200 import backend as be
 
@@ -183,7 +185,9 @@ class ThresholdLAB:
                     todo_errors = max_errors - before.errors
                     if todo_errors <= 0:
                         todo_shots = 0
-                shot0 = before.shots
+                # position in the RNG stream: recorded by our own rows; a foreign CSV only has the shot count
+                shot0 = int(before.custom_counts.get("next_shot", before.shots))
+            next_shot = shot0
             if todo_shots <= 0:
                 pass
             elif dem.num_errors == 0:
@@ -203,6 +207,8 @@ class ThresholdLAB:
                         dech, demh.tile_shots, seed + 1_000_003 * task_index, todo_shots, todo_errors,
                         int(opts.get("batch_shots", 0)), dist, rank, world, device, shot0=shot0,
                     )
+                    tile = demh.tile_shots
+                    next_shot = -(-shot0 // tile) * tile + -(-shots // tile) * tile
                 finally:
                     dech.close()
                     demh.close()
@@ -214,6 +220,7 @@ class ThresholdLAB:
                 errors=errors,
                 discards=discards,
                 seconds=time.perf_counter() - t0,
+                custom_counts={"next_shot": int(next_shot)} if save_resume_filepath else {},
             )
             if save_resume_filepath and rank == 0 and shots > 0:
                 append_stats_to_csv(save_resume_filepath, new)

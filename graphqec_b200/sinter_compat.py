@@ -60,6 +60,30 @@ class B200Decoder(_DecoderBase):
     def compile_decoder_for_dem(self, *, dem) -> B200CompiledDecoder:
         return B200CompiledDecoder(_as_model(dem), self.kind, self.device, **self.params)
 
+    def decode_via_files(self, *, num_shots: int, num_dets: int, num_obs: int, dem_path, dets_b8_in_path,
+                         obs_predictions_b8_out_path, tmp_dir=None) -> None:
+        """sinter's file form of the plug-in (``sinter.Decoder.decode_via_files``): the DEM as ``.dem`` text,
+        detection events as b8 rows (``ceil(num_dets / 8)`` bytes per shot), predictions written as b8 rows
+        (``ceil(num_obs / 8)`` bytes per shot)."""
+        with open(dem_path) as f:
+            model = DetectorErrorModel.from_text(f.read())
+        if model.num_detectors > num_dets or model.num_observables > num_obs:
+            raise ValueError("the DEM refers to more detectors / observables than the call declares")
+        model.num_detectors, model.num_observables = int(num_dets), int(num_obs)
+        db, ob = (num_dets + 7) // 8, (num_obs + 7) // 8
+        dets = np.fromfile(dets_b8_in_path, dtype=np.uint8)
+        if dets.size != num_shots * db:
+            raise ValueError(f"{dets_b8_in_path}: expected {num_shots} x {db} bytes, found {dets.size}")
+        compiled = B200CompiledDecoder(model, self.kind, self.device, **self.params)
+        try:
+            pred = compiled.decode_shots_bit_packed(bit_packed_detection_event_data=dets.reshape(num_shots, db))
+        finally:
+            compiled.dech.close()
+            compiled.demh.close()
+        out = np.zeros((num_shots, ob), dtype=np.uint8)
+        out[:, : pred.shape[1]] = pred[:, :ob]
+        out.tofile(obs_predictions_b8_out_path)
+
 
 class B200CompiledSampler(_CompiledSamplerBase):
     """Fused device path: sample + decode + count per call (sinter >= 1.14 ``CompiledSampler``)."""

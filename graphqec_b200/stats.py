@@ -67,6 +67,7 @@ class TaskStats:
     errors: int = 0
     discards: int = 0
     seconds: float = 0.0
+    custom_counts: dict = field(default_factory=dict)   # sinter's last CSV column; "next_shot" = RNG stream position
 
     def to_anon_stats(self) -> AnonTaskStats:
         return AnonTaskStats(self.shots, self.errors, self.discards, self.seconds)
@@ -74,9 +75,12 @@ class TaskStats:
     def to_csv_line(self) -> str:
         """One row in sinter's CSV schema (see ``CSV_HEADER``)."""
         meta = json.dumps(self.json_metadata, sort_keys=True, default=float).replace('"', '""')
+        custom = ""
+        if self.custom_counts:
+            custom = '"' + json.dumps(self.custom_counts, sort_keys=True).replace('"', '""') + '"'
         return (
             f"{self.shots:>10},{self.errors:>10},{self.discards:>10},{self.seconds:>8.3g},"
-            f"{self.decoder},{self.strong_id},\"{meta}\","
+            f"{self.decoder},{self.strong_id},\"{meta}\",{custom}"
         )
 
     @property
@@ -125,12 +129,19 @@ def read_stats_from_csv(path: str) -> list[TaskStats]:
             discards=int(row[col["discards"]]),
             seconds=float(row[col["seconds"]]),
         )
+        if "custom_counts" in header and len(row) > header.index("custom_counts"):
+            txt = row[header.index("custom_counts")].strip()
+            if txt:
+                inc.custom_counts = {str(k): int(v) for k, v in json.loads(txt).items()}
         if sid in merged:
             m = merged[sid]
             m.shots += inc.shots
             m.errors += inc.errors
             m.discards += inc.discards
             m.seconds += inc.seconds
+            for k, v in inc.custom_counts.items():
+                # "next_shot" is a position in the task's RNG stream (the furthest any recorded run got), not a count
+                m.custom_counts[k] = max(m.custom_counts.get(k, 0), v) if k == "next_shot" else m.custom_counts.get(k, 0) + v
         else:
             merged[sid] = inc
     return list(merged.values())

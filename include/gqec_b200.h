@@ -133,7 +133,9 @@ int gq_transpose_dm_to_sm(gq_dem *dem, const uint32_t *dm, uint32_t nbits, uint6
 int gq_transpose_sm_to_dm(gq_dem *dem, const uint32_t *sm, uint32_t nbits, uint64_t nshots, uint32_t *dm);
 
 /* ---- decoder: replaces sinter's compile_decoder_for_dem -> pymatching.Matching
- *      .from_detector_error_model(dem) (row A8) or stimbposd's BP (row A10, without OSD). */
+ *      .from_detector_error_model(dem) (row A8) or stimbposd's BP+OSD (row A10): min-sum BP, and with params.bp_osd
+ *      order-0 OSD for the shots BP leaves unconverged (stimbposd's default is product-sum BP + OSD-CS(60): the
+ *      BASELINE north star asks for min-sum; higher OSD orders are not built). */
 int gq_decoder_create(gq_dem *dem, int kind, const gq_decoder_params *params, gq_dec **out);
 void gq_decoder_destroy(gq_dec *dec);
 int gq_decoder_get_graph_info(const gq_dec *dec, gq_graph_info *info);
@@ -154,8 +156,11 @@ int gq_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *p
               int32_t *weight_out, uint8_t *flags_out, uint32_t *corr_out);
 
 /* ---- decode, device buffers in the detector-major bit-sliced layout of gq_extract (32 shots per word):
- *      dets_dm: dev uint32[D][ceil(nshots/32)] -> pred_dm: dev uint32[max(O,1)][ceil(nshots/32)]. */
-int gq_decode_dm(gq_dec *dec, const uint32_t *dets_dm, uint64_t nshots, uint32_t *pred_dm);
+ *      dets_dm: dev uint32[D][ceil(nshots/32)] -> pred_dm: dev uint32[max(O,1)][ceil(nshots/32)].
+ *      corr_sm (nullable; SURVEY 8b "corr_optional"; needs with_corrections): the corrections, shot-major like
+ *      gq_decode's corr_out -- dev uint32[nshots][ceil(num_edges/32)] (matching: edge set) or
+ *      [nshots][ceil(num_errors/32)] (BP: mechanism set).  Works through the batch in slices of 2^20 shots. */
+int gq_decode_dm(gq_dec *dec, const uint32_t *dets_dm, uint64_t nshots, uint32_t *pred_dm, uint32_t *corr_sm);
 
 /* ---- decode, host buffers in sinter's layout: the body of
  *      CompiledDecoder.decode_shots_bit_packed(bit_packed_detection_event_data=...).

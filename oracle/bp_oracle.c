@@ -77,7 +77,10 @@ int orc_bp_minsum(int D, int M, const uint32_t *chk_indptr, const uint32_t *chk_
  * answer is the unique combination of basis columns that equals the syndrome.  Because the representation
  * in a basis is unique, the walk may stop at the first moment the syndrome lies in the span of the basis
  * built so far: the later basis columns would get coefficient 0.  max_candidates bounds the walk
- * (0 = all M); max_basis bounds the basis size (0 = D).
+ * (0 = all M); max_basis bounds the basis size (0 = D).  max_candidates < 0 is the CUDA kernel's schedule:
+ * the first |max_candidates| variables of the reliability order, then EVERY variable in index order (so a
+ * syndrome in the column space of H is always reached; the tail is only entered when the reliability-ordered
+ * prefix did not suffice).
  * Returns 0 and the error vector on success, 1 if the syndrome was not reached within the bounds. */
 typedef struct { float key; uint32_t idx; } osd_item;
 static int osd_cmp(const void *a, const void *b) {
@@ -91,6 +94,8 @@ int orc_osd0(int D, int M, const uint32_t *chk_indptr, const uint32_t *chk_var, 
              const uint32_t *var_edge, const float *posterior, const uint8_t *syndrome, int max_candidates,
              int max_basis, uint8_t *out_err, int *basis_size, int *candidates_used) {
     const int W = (D + 63) / 64;
+    int tail = 0;
+    if (max_candidates < 0) { tail = M; max_candidates = -max_candidates; }
     if (max_candidates <= 0 || max_candidates > M) max_candidates = M;
     if (max_basis <= 0 || max_basis > D) max_basis = D;
     const int CW = (max_basis + 63) / 64;
@@ -126,8 +131,8 @@ int orc_osd0(int D, int M, const uint32_t *chk_indptr, const uint32_t *chk_var, 
         for (int w_ = 0; w_ < CW; ++w_) sc[w_] ^= coef[(size_t)piv[r_] * CW + w_];  \
     }
     REDUCE_S();
-    for (int i = 0; i < max_candidates && !done && nb < max_basis; ++i) {
-        const uint32_t c = items[i].idx;
+    for (int i = 0; i < max_candidates + tail && !done && nb < max_basis; ++i) {
+        const uint32_t c = i < max_candidates ? items[i].idx : (uint32_t)(i - max_candidates);
         used = i + 1;
         memset(v, 0, (size_t)W * 8); memset(vc, 0, (size_t)CW * 8);
         for (uint32_t k = var_indptr[c]; k < var_indptr[c + 1]; ++k) { uint32_t r = edge_chk[var_edge[k]]; v[r >> 6] ^= 1ull << (r & 63); }

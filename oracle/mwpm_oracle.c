@@ -10,7 +10,9 @@
  * restated here is PyMatching's published behaviour: exact
  * minimum-weight perfect matching with a boundary on the detector graph, weight ln((1-p)/p),
  * prediction = XOR of the observable masks along the matched shortest paths.  It is pinned
- * instead against networkx.min_weight_matching (tests/test_oracle_mwpm.py) and brute force.
+ * instead against networkx.max_weight_matching and brute force (tests/test_oracle.py), and -- through the
+ * whole pipeline -- against the error counts the reference's own sinter + PyMatching runs recorded
+ * (tests/test_gpu_reference_stats.py).
  *
  * Method (deliberately different from the CUDA decoder): all-pairs shortest paths by Dijkstra
  * at graph creation; per shot, the defects become a complete graph with weights

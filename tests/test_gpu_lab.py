@@ -72,6 +72,27 @@ def test_sinter_style_adapters():
     assert st.shots >= 10000 and 0 < st.errors < st.shots // 10
 
 
+def test_decode_via_files(tmp_path):
+    """sinter's file form of the decoder plug-in: .dem text + b8 detection events in, b8 predictions out."""
+    from graphqec_b200.sinter_compat import B200Decoder
+
+    code = RotatedSurfaceCode(distance=5, depolarize1_rate=0.006, depolarize2_rate=0.006)
+    code.build_memory_circuit(number_of_rounds=5)
+    dem = code.memory_circuit.detector_error_model(decompose_errors=True)
+    dets, obs = po.sample(dem, 3, 3001)
+    (tmp_path / "m.dem").write_text(str(dem))
+    dets.tofile(tmp_path / "dets.b8")
+    B200Decoder().decode_via_files(num_shots=3001, num_dets=dem.num_detectors, num_obs=dem.num_observables,
+                                   dem_path=tmp_path / "m.dem", dets_b8_in_path=tmp_path / "dets.b8",
+                                   obs_predictions_b8_out_path=tmp_path / "pred.b8", tmp_dir=tmp_path)
+    pred = np.fromfile(tmp_path / "pred.b8", dtype=np.uint8).reshape(3001, 1)
+    direct = B200Decoder().compile_decoder_for_dem(dem=dem).decode_shots_bit_packed(bit_packed_detection_event_data=dets)
+    assert (pred == direct).all()
+    with pytest.raises(ValueError):
+        B200Decoder().decode_via_files(num_shots=3000, num_dets=dem.num_detectors, num_obs=1, dem_path=tmp_path / "m.dem",
+                                       dets_b8_in_path=tmp_path / "dets.b8", obs_predictions_b8_out_path=tmp_path / "p2.b8")
+
+
 def test_bposd_name_runs_min_sum_bp():
     th = ThresholdLAB(configurations=[{"distance": 3}], code=RotatedSurfaceCode, error_rates=[0.002], decoder="bposd")
     th.collect_stats(max_shots=20000, max_errors=10**9)

@@ -416,7 +416,7 @@ def test_bp_osd_matches_oracle_bit_for_bit(name, nshots, iters):
     it_gpu, flags = it_gpu.cpu().numpy(), flags.cpu().numpy()
     n_osd = 0
     for s in range(nshots):
-        e, it, st, nb, used = orc.decode_osd(bits[s], max_candidates=2048, max_basis=1024)
+        e, it, st, nb, used = orc.decode_osd(bits[s], max_candidates=-2048)      # the kernel's schedule: 2048 ordered, then all
         assert it == it_gpu[s]
         assert (e == cb[s]).all(), (s, it, st)
         assert flags[s] == (1 if st == 1 else 0)
@@ -537,6 +537,32 @@ def test_north_star_corrections_at_scale():
     dech.close()
 
 
+def test_osd_walks_past_the_ordered_candidates_when_it_must():
+    """2100 likely decoys that all flip D0 fill the 2048 reliability-ordered candidate slots; the syndrome (D1) needs one
+    of ten symmetric, unlikely mechanisms behind them (BP cannot break their symmetry): the kernel goes on through all
+    variables in index order -- like the oracle's max_candidates = -2048 schedule, bit for bit -- instead of giving up."""
+    import torch
+    lines = ["error(0.45) D0"] * 2100 + ["error(0.01) D1"] * 10 + ["error(0.01) D1 D2 L0", "error(0.02) D2"]
+    dem = gq.DetectorErrorModel.from_text("\n".join(lines))
+    demh = be.DemHandle(dem, device=0)
+    bp = be.DecoderHandle(demh, be.BP_MINSUM, bp_max_iter=3, bp_alpha=0.9, bp_osd=True)
+    orc = po.BpOracle(dem, max_iter=3, alpha=0.9)
+    rows = np.array([[0b010], [0b110], [0b011], [0b000]], dtype=np.uint32)
+    t = torch.from_numpy(rows.view(np.int32)).cuda()
+    pred, it_gpu, flags, corr = bp.decode(t, want_weights=True, want_flags=True, want_corrections=True)
+    cb = np.unpackbits(corr.cpu().numpy().view(np.uint8).reshape(len(rows), -1), axis=1, bitorder="little")[:, : dem.num_errors]
+    walked_past = 0
+    for s, row in enumerate(rows[:, 0]):
+        syn = np.array([(row >> k) & 1 for k in range(3)], dtype=np.uint8)
+        e, it, st, nb, used = orc.decode_osd(syn, max_candidates=-2048)
+        assert it == int(it_gpu[s]) and (e == cb[s]).all() and int(flags[s]) == (1 if st == 1 else 0)
+        assert st != 1
+        walked_past += used > 2048
+    assert walked_past >= 2
+    assert orc.decode_osd(np.array([0, 1, 0], dtype=np.uint8), max_candidates=2048)[2] == 1     # the capped walk gives up
+    bp.close(); demh.close()
+
+
 def test_bb144_bposd_corrections_at_scale():
     """BASELINE configs[4] at its full size (BB [[144,12,12]], 12 rounds: 1728 detectors, 67 752 mechanisms): BP + OSD-0
     gives every shot a correction that reproduces its syndrome (H . e == s), the prediction is L . e, and almost no
@@ -571,6 +597,23 @@ def test_bb144_bposd_corrections_at_scale():
     bp.close(); osd.close(); demh.close()
 
 
+def test_bb144_at_p3e3_every_shot_gets_a_valid_correction():
+    """Round 1 capped the OSD basis at 1024 columns and the walk at 2048 candidates: 0.5 % of the shots at p = 3e-3 kept
+    BP's unconverged decision.  With the basis sized by D and the walk continuing past the ordered candidates, all do."""
+    code = gq.BivariateBicycleCode(depolarize1_rate=0.003, depolarize2_rate=0.003)
+    code.build_memory_circuit(number_of_rounds=12, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model()
+    demh = be.DemHandle(dem, device=0)
+    osd = be.DecoderHandle(demh, be.BP_MINSUM, bp_max_iter=30, bp_osd=True)
+    n = 4096
+    dets, obs = demh.sample(9, 0, n)
+    pred, iters, flags = osd.decode(dets, want_weights=True, want_flags=True)
+    assert int((flags != 0).sum().item()) == 0
+    shots, errors, discards = osd.collect(9, 0, n, 0)
+    assert (shots, discards) == (n, 0) and errors == int((pred != obs).any(dim=1).sum().item())
+    osd.close(); demh.close()
+
+
 @pytest.mark.parametrize("kind,d,p,nshots", [("UnrotatedSurfaceCode", 15, 0.003, 160), ("RotatedSurfaceCode", 17, 0.005, 96)])
 def test_large_codes_match_the_oracle(kind, d, p, nshots):
     """BASELINE configs[2] (unrotated d = 15, 15 rounds: 6300 detectors, ~270 defects per shot) and a d = 17 point of the
@@ -600,3 +643,13 @@ def test_decode_dm_equals_decode_sm():
     dets_dm = demh.sm_to_dm(dets, demh.D, n)
     pred_dm = dech.decode_dm(dets_dm, n)
     assert (demh.dm_to_sm(pred_dm, 1, n) == pred).all()
+    # SURVEY 8b "corr_optional": the same corrections as the shot-major entry point
+    pred2, _, _, corr = dech.decode(dets, want_weights=True, want_flags=True, want_corrections=True)
+    pred_dm2, corr_dm = dech.decode_dm(dets_dm, n, want_corrections=True)
+    assert (pred_dm2 == pred_dm).all() and (corr_dm == corr).all()
+    # more shots than one 2^20-shot slice, ragged: the slices are gathered / scattered on word boundaries
+    dem, demh, dech = case("rep3")
+    n = (1 << 20) + 5 * demh.tile_shots + 19
+    dets, obs = demh.sample(56, 0, n)
+    pred_dm = dech.decode_dm(demh.sm_to_dm(dets, demh.D, n), n)
+    assert (demh.dm_to_sm(pred_dm, 1, n) == dech.decode(dets)).all()

@@ -165,3 +165,13 @@ def test_collect_stats_resumes_from_csv(tmp_path, monkeypatch):
     assert th.samples[0].shots == 50000
     assert len(open(path).read().splitlines()) == 3      # header + one row per run that did work
     assert first[0][0] == 0
+    # budgets that are not tile multiples -- run 1 used [0, 20000), run 2 [20224, 50224); a third run must
+    # start behind 50224 (next_shot recorded per row), not at ceil(50000 / 256) * 256 = 50176, which run 2 already drew
+    calls.clear()
+    th.collect_stats(max_shots=60000, max_errors=0, save_resume_filepath=path)
+    run2_end = -(-20000 // 256) * 256 + -(-30000 // 256) * 256
+    assert calls[0][0] == run2_end and calls[0][0] >= 20224 + 30000
+    assert th.samples[0].shots == 60000 and th.samples[0].custom_counts["next_shot"] == run2_end + -(-10000 // 256) * 256
+    from graphqec_b200.stats import read_stats_from_csv
+    merged = read_stats_from_csv(path)[0]
+    assert merged.shots == 60000 and merged.custom_counts["next_shot"] == th.samples[0].custom_counts["next_shot"]
