@@ -71,14 +71,15 @@ struct gq_dec {
     double timing[8] = {0};
     double kprof[4] = {0};             // dominant first-tier kernel of the last call: {ms, launches, shots, K}
     cudaEvent_t kev0 = nullptr, kev1 = nullptr;
-    cudaStream_t side_streams[12] = {};   // first tier: the smaller classes' kernels
-    cudaEvent_t side_done[12] = {};
+    cudaStream_t side_streams[16] = {};   // first tier: the smaller classes' kernels
+    cudaEvent_t side_done[16] = {};
     // ---- matching
     uint32_t num_edges = 0, num_boundary = 0;
     std::vector<uint32_t> eu, ev, ew;
     std::vector<uint64_t> eobs;
     std::vector<double> eprob;
     uint32_t fast_cap = 0, max_cap = 0, max_dist = 0;
+    bool big_classes = false;          // first-tier classes K = 48, 64 (1025 .. 2048 defects) usable: max_dist < 2^15
     uint16_t *d_dist = nullptr;        // [D][D+1]
     uint8_t *d_pobs = nullptr;         // [D][D+1] observable mask of the shortest path
     uint32_t *d_nbr = nullptr;         // [D+2][NBR_LEN] nearest detectors of each detector (distance << 16 | detector)
@@ -118,13 +119,14 @@ struct gq_dec {
 };
 
 // first-tier classes of the matching decoder (matching.cu): K = ceil(defects / 32) slots per lane; classes 0..7: K = 1..8
-// (up to 256 defects), 8..10: K = 10, 12, 16 (up to 512), 11, 12: K = 24, 32 (up to 1024); GQ_MT_CLASSES = beyond the tier.
+// (up to 256 defects), 8..10: K = 10, 12, 16 (up to 512), 11, 12: K = 24, 32 (up to 1024), 13, 14: K = 48, 64 (up to 2048;
+// most of the per-lane state lives in local memory there); GQ_MT_CLASSES = beyond the tier.
 // Shared with the sampler and the b8 re-stride kernel, which classify the shots they write (no separate pass).
-static constexpr int GQ_MT_CLASSES = 13;
-static constexpr int GQ_MT_CAP = 1024;
+static constexpr int GQ_MT_CLASSES = 15;
+static constexpr int GQ_MT_CAP = 2048;
 __host__ __device__ constexpr int gq_mt_class_of(int n) {   // n >= 1 defects
     return n <= 256 ? (n - 1) >> 5
-                    : (n <= 320 ? 8 : (n <= 384 ? 9 : (n <= 512 ? 10 : (n <= 768 ? 11 : (n <= 1024 ? 12 : GQ_MT_CLASSES)))));
+                    : (n <= 320 ? 8 : (n <= 384 ? 9 : (n <= 512 ? 10 : (n <= 768 ? 11 : (n <= 1024 ? 12 : (n <= 1536 ? 13 : (n <= 2048 ? 14 : GQ_MT_CLASSES)))))));
 }
 struct GqClassifyOut {
     uint32_t *counts = nullptr;     // [GQ_MT_CLASSES] shots per class (null: no classification)

@@ -41,7 +41,7 @@ typedef unsigned __int128 gqw_mask;   // one bit per slot; the single host lane 
 #else
 #define GQW_LANES 32
 #define GQW_LOG 5
-typedef unsigned gqw_mask;
+typedef unsigned long long gqw_mask;   // one bit per slot of a lane (K <= 64)
 #endif
 #define GQW_FULL 0xffffffffu
 #define GQW_BIT(k) ((gqw_mask)1 << (k))
@@ -176,13 +176,14 @@ __device__ __forceinline__ int sel_slot(const TV (&arr)[K], const int slot) {
 // Label of a slot = the key bits it contributes: kb = vertex (unlabelled), vertex | 0x100 (outer),
 // vertex | bit 31 (inner).  With X = 4w - y_u + (D - yb[k]) the candidate time of an edge from outer u
 // is X for unlabelled and inner targets (time resp. frozen slack) and X / 2 for outer ones.
-// Field widths: the vertex takes VB = 8 bits up to 256 defects per shot, 9 bits up to 512 and 10 bits up to 1024,
-// the type 2 bits above it, the time the rest below bit 31 (21, 20 resp. 19 bits; times stay below 2^19: they are
-// bounded by 8 x the largest table distance, a u16).
+// Field widths: the vertex takes VB = 8 bits up to 256 defects per shot, 9 bits up to 512, 10 bits up to 1024 and 11 bits
+// up to 2048, the type 2 bits above it, the time the rest below bit 31 (21, 20, 19 resp. 18 bits; times are bounded by
+// 8 x the largest table distance, a u16: below 2^19 always, below 2^18 when that distance is below 2^15 -- the host only
+// uses the 11-bit classes then).
 static const unsigned EK_NONE = 0x7fffffffu;   // no pending edge event (time field all ones)
 static const unsigned EK_FROZEN = 0x80000000u;
 template <int K> struct KeyBits {
-    static constexpr int VB = (K * GQW_LANES > 512) ? 10 : ((K * GQW_LANES > 256) ? 9 : 8);
+    static constexpr int VB = (K * GQW_LANES > 1024) ? 11 : ((K * GQW_LANES > 512) ? 10 : ((K * GQW_LANES > 256) ? 9 : 8));
     static constexpr int TS = VB + 2;
     static constexpr unsigned VM = (1u << VB) - 1u;
     static constexpr unsigned TY1 = 1u << VB, TY2 = 2u << VB, TY3 = 3u << VB;

@@ -341,13 +341,15 @@ __global__ void __launch_bounds__(256, (K <= 4 ? GQ_PER_SM : 2)) match_fast_kern
                             // kernels share the instruction cache: measured slower once start/solve were split)
 #endif
 // classes 0..7: K = 1..8 (8-bit vertex field, up to 256 defects); 8..10: K = 10, 12, 16 (9-bit field, up to 512);
-// 11, 12: K = 24, 32 (10-bit field, up to 1024; part of the per-lane state lives in local memory there)
+// 11, 12: K = 24, 32 (10-bit field, up to 1024; part of the per-lane state lives in local memory there);
+// 13, 14: K = 48, 64 (11-bit field, up to 2048: d = 23 up to p = 1e-2, the reference example's largest point; only when
+// the event times fit the 18-bit field that leaves, gq_dec::big_classes)
 static constexpr int MT_CLASSES = GQ_MT_CLASSES;
 static constexpr int MT_CAP = GQ_MT_CAP;
 __host__ __device__ constexpr int mt_class_of(int n) { return gq_mt_class_of(n); }   // n >= 1 defects -> class, MT_CLASSES = beyond the first tier
 template <int K> struct MtClassRange {     // defect counts a class-K list may hold: (LO, 32 K]
-    static constexpr int LO = K <= 8 ? 32 * (K - 1) : (K == 10 ? 256 : (K == 12 ? 320 : (K == 16 ? 384 : (K == 24 ? 512 : 768))));
-    static constexpr int WPB = K <= 16 ? 8 : 4;   // warps per block: the K = 24, 32 forests are 30 .. 41 KB per warp
+    static constexpr int LO = K <= 8 ? 32 * (K - 1) : (K == 10 ? 256 : (K == 12 ? 320 : (K == 16 ? 384 : (K == 24 ? 512 : (K == 32 ? 768 : (K == 48 ? 1024 : 1536))))));
+    static constexpr int WPB = K <= 16 ? 8 : (K <= 32 ? 4 : 2);   // warps per block: the forests are 30 .. 41 KB per warp at K = 24, 32 and 61 .. 82 KB at K = 48, 64
 };
 
 #ifndef GQ_DYNAMIC
@@ -545,6 +547,15 @@ __global__ void __launch_bounds__(32 * MtClassRange<K>::WPB, (K <= 3 ? GQ_MT_PER
     }
 }
 
+// classes 13, 14 of a decoder whose event times do not fit the 18-bit field: their shots join the overflow list
+__global__ void append_list_to_overflow_kernel(const uint32_t *list, uint32_t n, uint32_t *overflow, uint32_t overflow_cap, uint32_t maxdef) {
+    __shared__ uint32_t base;
+    if (threadIdx.x == 0) { base = atomicAdd(&overflow[0], n); atomicMax(&overflow[1], maxdef); }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        if (base + i < overflow_cap) overflow[2 + base + i] = list[i];
+}
+
 template <int K>
 static int launch_tree_class(MatchArgs b, uint32_t *cursors, gq_dem *dem, cudaStream_t st, int *launches, cudaEvent_t ev0, cudaEvent_t ev1) {
     constexpr int WPB = MtClassRange<K>::WPB;
@@ -586,7 +597,9 @@ static size_t start_record_bytes(int c) {   // class c = K - 1
     case 9: return sizeof(StartRecord<12>);
     case 10: return sizeof(StartRecord<16>);
     case 11: return sizeof(StartRecord<24>);
-    default: return sizeof(StartRecord<32>);
+    case 12: return sizeof(StartRecord<32>);
+    case 13: return sizeof(StartRecord<48>);
+    default: return sizeof(StartRecord<64>);
     }
 }
 
@@ -726,6 +739,7 @@ int gq_matching_create(gq_dec *dec) {
     if (too_far) GQ_FAIL(GQ_E_UNSUPPORTED, "matching decoder: path lengths exceed 16 bits; lower weight_levels");
     for (uint32_t s = 0; s < N; ++s) dist[(size_t)s * NT + s] = 0xFFFFu;   // no self pairs (match_tree.cuh relies on it)
     dec->max_dist = *std::max_element(row_max.begin(), row_max.end());
+    dec->big_classes = dec->max_dist < 32768u;   // event times (<= 8 x a table distance) fit the 18 bits an 11-bit vertex field leaves
     // ---- the NBR_LEN nearest other detectors of every detector (ascending distance, ties by index) for the
     // first tier's dual start; rows D and D + 1 and the tails are padding (see match_tree.cuh)
     const uint32_t pad_entry = (0xFFFFu << 16) | (32u * dem->DW);
@@ -798,7 +812,7 @@ int gq_matching_create(gq_dec *dec) {
     if (configure_tree_class<1>() || configure_tree_class<2>() || configure_tree_class<3>() || configure_tree_class<4>() ||
         configure_tree_class<5>() || configure_tree_class<6>() || configure_tree_class<7>() || configure_tree_class<8>() ||
         configure_tree_class<10>() || configure_tree_class<12>() || configure_tree_class<16>() ||
-        configure_tree_class<24>() || configure_tree_class<32>())
+        configure_tree_class<24>() || configure_tree_class<32>() || configure_tree_class<48>() || configure_tree_class<64>())
         GQ_FAIL(GQ_E_CUDA, "matching decoder: cudaFuncSetAttribute failed for the first-tier kernels");
     GQ_CUDA(cudaMalloc((void **)&dec->d_lists, (size_t)(MT_CLASSES * ((size_t)1 << GQ_SLICE_LOG2) + 64) * 4));
     for (int i = 0; i < MT_CLASSES - 1; ++i) {
@@ -915,6 +929,12 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
             for (int oi = 0; oi < MT_CLASSES; ++oi) {
                 const int c = order[oi];
                 if (counts[c] == 0) continue;
+                if (c >= 13 && !dec->big_classes) {
+                    append_list_to_overflow_kernel<<<1, 1024, 0, dem->stream>>>(d_lists + (size_t)c * slice, counts[c], ovf_buf[cur], dec->overflow_cap, c == 13 ? 1536u : 2048u);
+                    GQ_CUDA(cudaGetLastError());
+                    ++*launches;
+                    continue;
+                }
                 cudaStream_t st = (oi == 0 || !dec->side_streams[0] || !GQ_SIDE_STREAMS) ? dem->stream : dec->side_streams[nside++];
                 b.list = d_lists + (size_t)c * slice; b.nitems = counts[c];
                 b.ws = (char *)dec->d_recs + rec_off[c]; b.ws_stride = start_record_bytes(c);
@@ -932,7 +952,9 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
                 case 9: lrc = launch_tree_class<12>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 case 10: lrc = launch_tree_class<16>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 case 11: lrc = launch_tree_class<24>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
-                default: lrc = launch_tree_class<32>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 12: lrc = launch_tree_class<32>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                case 13: lrc = launch_tree_class<48>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
+                default: lrc = launch_tree_class<64>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 }
                 if (lrc) GQ_FAIL(lrc, "matching decoder: first-tier kernel launch failed");
                 if (st != dem->stream) {
@@ -946,7 +968,7 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
             if (counts[dom]) {
                 float ms = 0;
                 cudaEventElapsedTime(&ms, dec->kev0, dec->kev1);
-                dec->kprof[0] += ms; dec->kprof[1] += 1; dec->kprof[2] += counts[dom]; dec->kprof[3] = dom < 8 ? dom + 1 : (dom == 8 ? 10 : (dom == 9 ? 12 : (dom == 10 ? 16 : (dom == 11 ? 24 : 32))));
+                dec->kprof[0] += ms; dec->kprof[1] += 1; dec->kprof[2] += counts[dom]; dec->kprof[3] = dom < 8 ? dom + 1 : (dom == 8 ? 10 : (dom == 9 ? 12 : (dom == 10 ? 16 : (dom == 11 ? 24 : (dom == 12 ? 32 : (dom == 13 ? 48 : 64))))));
             }
             if (ovf[0] == 0) continue;
             if (ovf[0] > dec->overflow_cap) GQ_FAIL(GQ_E_INTERNAL, "matching decoder: overflow list overrun");

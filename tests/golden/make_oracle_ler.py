@@ -20,7 +20,7 @@ CONFIGS = [
     ("UnrotatedSurfaceCode", {"distance": 5}, 0.008, 100000),
     ("RotatedSurfaceCode", {"distance": 9}, 0.005, 200000),
     ("RotatedSurfaceCode", {"distance": 11}, 0.005, 600000),
-    ("RotatedSurfaceCode", {"distance": 11}, 0.005, 2400000),    # the north-star point, tighter interval
+    # (the north-star point at >= 10^7 shots: make_oracle_ler_fine.py -> oracle_ler_fine.json)
     ("RotatedSurfaceCode", {"distance": 11}, 0.008, 300000),     # 129 defects per shot: classes K = 4 .. 6
     # BASELINE configs[3]: Steane code through CssCode, low-p tail (the matching graph ignores the hyperedges, as PyMatching does)
     ("CssCode", {"Hx": [[1, 1, 1, 1, 0, 0, 0], [0, 1, 1, 0, 1, 1, 0], [0, 0, 1, 1, 0, 1, 1]],

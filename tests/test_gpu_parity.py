@@ -315,6 +315,32 @@ def test_every_first_tier_class_and_the_ladder_give_the_optimum():
     assert (dech.decode(t) == pred).all()
 
 
+def test_first_tier_classes_up_to_2048_defects():
+    """classes K = 48, 64 (11-bit vertex keys, 1025 .. 2048 defects per shot: rotated d = 23 up to p = 1e-2, the largest
+    point of the reference's example) and the ladder beyond them, on random syndromes of the rotated d = 17 graph"""
+    import torch
+    code = gq.RotatedSurfaceCode(distance=17, depolarize1_rate=0.005, depolarize2_rate=0.005)
+    code.build_memory_circuit(number_of_rounds=17, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model(decompose_errors=True)
+    demh = be.DemHandle(dem, device=0)
+    dech = be.DecoderHandle(demh, be.MATCHING)
+    assert dech.graph_info.max_distance < 32768
+    rng = np.random.default_rng(5)
+    D = dem.num_detectors
+    counts = [1024, 1025, 1300, 1536, 1537, 1800, 2047, 2048, 2049, 2300]
+    rows = np.zeros((len(counts), demh.DW), dtype=np.uint32)
+    for i, c in enumerate(counts):
+        for k in rng.choice(D, size=c, replace=False):
+            rows[i, k >> 5] |= np.uint32(1) << np.uint32(k & 31)
+    t = torch.from_numpy(rows.view(np.int32)).cuda()
+    pred, wts, flags = dech.decode(t, want_weights=True, want_flags=True)
+    orc = po.MwpmOracle(dem)
+    opred, owts = orc.decode_batch(b8(t, D), nthreads=len(counts), return_weights=True)
+    assert (flags == 0).all() and (wts.cpu().numpy() == owts).all()
+    assert (dech.decode(t) == pred).all()
+    dech.close(); demh.close()
+
+
 def test_count_and_collect_agree():
     dem, demh, dech = case("rot5")
     n = 40 * demh.tile_shots
