@@ -59,6 +59,7 @@ struct BpArgs {
 };
 
 
+static constexpr int BP_BATCH = 8;        // shots per block of the global-scratch (shot-interleaved) BP kernel
 static constexpr int OSD_NCAND = 2048;    // reliability-ordered candidates kept per shot (BB-144 at p = 3e-3: up to ~1400 are usually walked,
                                           // basis <= ~650); a shot that needs more goes on through all variables in index order
 // the basis can grow to rank(H) <= D columns: coefficient sets are WPL words per lane like the vectors themselves
@@ -71,7 +72,7 @@ __device__ __forceinline__ uint32_t osd_key(float x) {   // order-preserving map
 
 // The k variables with the smallest posterior, ascending (ties by index), written to out[0..k); k <= OSD_NCAND.
 // All 256 threads of the block call it; tot[] holds the block's M posteriors.
-__device__ void osd_select(const float *tot, uint32_t M, uint32_t k, uint32_t *out) {
+__device__ void osd_select(const float *tot, uint32_t stride, uint32_t M, uint32_t k, uint32_t *out) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_rank;
     __shared__ uint32_t cnt_less[256], cnt_tie[256];
@@ -85,7 +86,7 @@ __device__ void osd_select(const float *tot, uint32_t M, uint32_t k, uint32_t *o
         hist[tid] = 0;
         __syncthreads();
         for (uint32_t v = tid; v < M; v += 256) {
-            const uint32_t key = osd_key(tot[v]);
+            const uint32_t key = osd_key(tot[(size_t)v * stride]);
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -103,7 +104,7 @@ __device__ void osd_select(const float *tot, uint32_t M, uint32_t k, uint32_t *o
     // ---- index-ordered compaction: thread t owns the contiguous chunk [t * C, (t + 1) * C)
     const uint32_t C = (M + 255) / 256, lo = tid * C, hi = min(M, lo + C);
     uint32_t nl = 0, nt = 0;
-    for (uint32_t v = lo; v < hi; ++v) { const uint32_t key = osd_key(tot[v]); nl += key < kth; nt += key == kth; }
+    for (uint32_t v = lo; v < hi; ++v) { const uint32_t key = osd_key(tot[(size_t)v * stride]); nl += key < kth; nt += key == kth; }
     cnt_less[tid] = nl; cnt_tie[tid] = nt;
     if (tid == 0) s_fill = 0;
     for (uint32_t i = tid; i < OSD_NCAND; i += 256) pairs[i] = ~0ull;
@@ -111,7 +112,7 @@ __device__ void osd_select(const float *tot, uint32_t M, uint32_t k, uint32_t *o
     uint32_t tie_before = 0;
     for (int t = 0; t < tid; ++t) tie_before += cnt_tie[t];
     for (uint32_t v = lo; v < hi; ++v) {
-        const uint32_t key = osd_key(tot[v]);
+        const uint32_t key = osd_key(tot[(size_t)v * stride]);
         bool take = key < kth;
         if (key == kth) { take = tie_before < need_ties; ++tie_before; }
         if (take) pairs[atomicAdd(&s_fill, 1u)] = ((unsigned long long)key << 32) | v;
@@ -287,11 +288,194 @@ __global__ void __launch_bounds__(256) bp_kernel(BpArgs a) {
             __shared__ uint32_t s_slot;
             if (tid == 0) { s_slot = atomicAdd(a.fail_count, 1u); a.fail_list[s_slot] = (uint32_t)shot; }
             __syncthreads();
-            osd_select(tot, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_NCAND);
+            osd_select(tot, 1u, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_NCAND);
         }
     }
 }
 
+
+// ---- big models (messages in global scratch): S shots per block with SHOT-INTERLEAVED messages, c2v[edge][S] and
+// tot[variable][S].  The passes are gathers through the Tanner graph's index lists -- posteriors by variable in the
+// check pass, messages by edge id in the variable pass -- and a 4-byte gather costs a whole 32-byte sector of HBM / L2
+// traffic; with eight shots side by side every gathered sector is eight useful floats (measured on BB-144: the
+// one-shot-per-block kernel moved 162 MB per shot at 3.0 TB/s).  The index lists are read once per S shots.
+// Arithmetic per shot is unchanged (same order of every sum, same tie rules), so decisions and iteration counts stay
+// bit-identical to oracle/bp_oracle.c.  A shot that converges is finalised at once (prediction, correction, iteration
+// count); the block goes on until all its shots are done or out of iterations -- at BB-144 error rates most shots that
+// converge do so within a few iterations of each other and four in five never do (they go to OSD).
+template <int S>
+__global__ void __launch_bounds__(256) bp_batched_kernel(BpArgs a) {
+    extern __shared__ uint32_t s_syn[];          // [S][DW] the group's syndromes
+    __shared__ uint32_t s_notconv, s_obs, s_slot;
+    float *c2v = a.scratch + (size_t)blockIdx.x * a.scratch_stride;   // [nnz][S]
+    float *tot = c2v + (size_t)a.nnz * S;                             // [M][S]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    const uint64_t ngroups = (a.nshots + S - 1) / S;
+
+    for (uint64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const uint64_t shot0 = grp * S;
+        const int ns = (int)min((uint64_t)S, a.nshots - shot0);
+        for (uint32_t i = tid; i < (uint32_t)S * a.DW; i += blockDim.x) {
+            const uint32_t sh = i / a.DW, w = i - sh * a.DW;
+            s_syn[i] = (int)sh < ns ? a.dets[(shot0 + sh) * a.DW + w] : 0u;
+        }
+        {
+            float4 *c4 = reinterpret_cast<float4 *>(c2v);
+            const size_t n4 = (size_t)a.nnz * S / 4;
+            for (size_t i = tid; i < n4; i += blockDim.x) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (uint32_t v = tid; v < a.M; v += blockDim.x) {
+            const float pr = a.prior[v];
+#pragma unroll
+            for (int sh = 0; sh < S; ++sh) tot[(size_t)v * S + sh] = pr;
+        }
+        __syncthreads();
+        uint32_t active = (1u << ns) - 1u;       // shots still iterating (block-uniform)
+        uint32_t unconverged = 0;                // shots that ran out of iterations
+
+        // writes the outcome of shot sh from the current posteriors (all threads)
+        auto finalise = [&](int sh, bool converged, int used) {
+            if (tid == 0) s_obs = 0;
+            __syncthreads();
+            const uint64_t shot = shot0 + sh;
+            uint32_t om = 0;
+            for (uint32_t v0 = 0; v0 < a.M; v0 += blockDim.x) {
+                const uint32_t v = v0 + tid;
+                const int bit = v < a.M && tot[(size_t)v * S + sh] < 0.0f;
+                if (bit) om ^= a.var_obs[v];
+                if (a.corr_out) {
+                    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+                    if (lane == 0 && (v >> 5) < a.MW) a.corr_out[shot * a.MW + (v >> 5)] = word;
+                }
+            }
+            om = __reduce_xor_sync(0xffffffffu, om);
+            if (lane == 0 && om) atomicXor(&s_obs, om);
+            __syncthreads();
+            if (tid == 0) {
+                a.pred[shot * a.OW] = s_obs;
+                for (uint32_t w = 1; w < a.OW; ++w) a.pred[shot * a.OW + w] = 0;
+                if (a.iters_out) a.iters_out[shot] = converged ? used : -a.max_iter;
+                if (a.flags_out) a.flags_out[shot] = converged ? 0 : 1;
+            }
+            __syncthreads();
+        };
+
+        for (int it = 1; it <= a.max_iter + 1 && active; ++it) {
+            if (tid == 0) s_notconv = 0;
+            __syncthreads();
+            // ---- check pass (+ parity of the current decisions)
+            for (uint32_t c = wid; c < a.D; c += nw) {
+                const uint32_t b = a.chk_ptr[c], e = a.chk_ptr[c + 1];
+                uint32_t scbits = 0;
+#pragma unroll
+                for (int sh = 0; sh < S; ++sh) scbits |= ((s_syn[sh * a.DW + (c >> 5)] >> (c & 31)) & 1u) << sh;
+                float m1[S], m2[S];
+                uint32_t arg[S], sg = 0, par = 0;
+#pragma unroll
+                for (int sh = 0; sh < S; ++sh) { m1[sh] = INFINITY; m2[sh] = INFINITY; arg[sh] = 0xFFFFFFFFu; }
+                for (uint32_t k = b + lane; k < e; k += 32) {
+                    const uint32_t v = a.chk_var[k];
+                    float t[S], cc[S];
+#pragma unroll
+                    for (int q = 0; q < S / 4; ++q) {
+                        const float4 x = reinterpret_cast<const float4 *>(tot + (size_t)v * S)[q];
+                        const float4 y = reinterpret_cast<const float4 *>(c2v + (size_t)k * S)[q];
+                        t[4 * q] = x.x; t[4 * q + 1] = x.y; t[4 * q + 2] = x.z; t[4 * q + 3] = x.w;
+                        cc[4 * q] = y.x; cc[4 * q + 1] = y.y; cc[4 * q + 2] = y.z; cc[4 * q + 3] = y.w;
+                    }
+#pragma unroll
+                    for (int sh = 0; sh < S; ++sh) {
+                        const float m = t[sh] - cc[sh], av = fabsf(m);
+                        sg ^= (uint32_t)(m < 0.0f) << sh;
+                        par ^= (uint32_t)(t[sh] < 0.0f) << sh;
+                        if (av < m1[sh]) { m2[sh] = m1[sh]; m1[sh] = av; arg[sh] = k; }
+                        else if (av < m2[sh]) m2[sh] = av;
+                    }
+                }
+                sg = __reduce_xor_sync(0xffffffffu, sg);
+                par = __reduce_xor_sync(0xffffffffu, par);
+                float g1[S], g2[S];
+                uint32_t garg[S];
+#pragma unroll
+                for (int sh = 0; sh < S; ++sh) {
+                    // magnitudes are >= 0 (or +inf): their bit patterns order like the floats
+                    g1[sh] = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(m1[sh])));
+                    garg[sh] = __reduce_min_sync(0xffffffffu, m1[sh] == g1[sh] ? arg[sh] : 0xFFFFFFFFu);
+                    const float x = (arg[sh] == garg[sh]) ? m2[sh] : m1[sh];
+                    g2[sh] = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(x)));
+                }
+                if (lane == 0) {
+                    const uint32_t bad = (par ^ scbits) & active;
+                    if (bad) atomicOr(&s_notconv, bad);
+                }
+                for (uint32_t k = b + lane; k < e; k += 32) {
+                    const uint32_t v = a.chk_var[k];
+                    float o[S];
+#pragma unroll
+                    for (int q = 0; q < S / 4; ++q) {
+                        const float4 x = reinterpret_cast<const float4 *>(tot + (size_t)v * S)[q];
+                        const float4 y = reinterpret_cast<const float4 *>(c2v + (size_t)k * S)[q];
+                        o[4 * q] = x.x - y.x; o[4 * q + 1] = x.y - y.y; o[4 * q + 2] = x.z - y.z; o[4 * q + 3] = x.w - y.w;
+                    }
+#pragma unroll
+                    for (int sh = 0; sh < S; ++sh) {
+                        const float mag = (k == garg[sh]) ? g2[sh] : g1[sh];
+                        const uint32_t sgn = ((scbits >> sh) ^ (sg >> sh) ^ (uint32_t)(o[sh] < 0.0f)) & 1u;
+                        o[sh] = a.alpha * (sgn ? -mag : mag);
+                    }
+#pragma unroll
+                    for (int q = 0; q < S / 4; ++q)
+                        reinterpret_cast<float4 *>(c2v + (size_t)k * S)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                }
+            }
+            __syncthreads();
+            const uint32_t notconv = s_notconv;
+            if (it > 1) {
+                uint32_t newly = active & ~notconv;   // their decision reproduces the syndrome: converged after it - 1 iterations
+                active &= notconv;
+                while (newly) {
+                    const int sh = __ffs(newly) - 1;
+                    newly &= newly - 1;
+                    finalise(sh, true, it - 1);
+                }
+            }
+            if (it == a.max_iter + 1) { unconverged = active; break; }
+            if (!active) break;
+            // ---- variable pass (every sum in the oracle's order)
+            for (uint32_t v = tid; v < a.M; v += blockDim.x) {
+                float t[S];
+                const float pr = a.prior[v];
+#pragma unroll
+                for (int sh = 0; sh < S; ++sh) t[sh] = pr;
+                const uint32_t b1 = a.var_ptr[v], e1 = a.var_ptr[v + 1];
+                for (uint32_t k = b1; k < e1; ++k) {
+                    const uint32_t ed = a.var_edge[k];
+#pragma unroll
+                    for (int q = 0; q < S / 4; ++q) {
+                        const float4 y = reinterpret_cast<const float4 *>(c2v + (size_t)ed * S)[q];
+                        t[4 * q] += y.x; t[4 * q + 1] += y.y; t[4 * q + 2] += y.z; t[4 * q + 3] += y.w;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < S / 4; ++q)
+                    reinterpret_cast<float4 *>(tot + (size_t)v * S)[q] = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+            }
+            __syncthreads();
+        }
+        // ---- shots that ran out of iterations: BP's last decision, and the hand-off to OSD-0
+        while (unconverged) {
+            const int sh = __ffs(unconverged) - 1;
+            unconverged &= unconverged - 1;
+            finalise(sh, false, a.max_iter);
+            if (a.osd_k) {
+                if (tid == 0) { s_slot = atomicAdd(a.fail_count, 1u); a.fail_list[s_slot] = (uint32_t)(shot0 + sh); }
+                __syncthreads();
+                osd_select(tot + sh, (uint32_t)S, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_NCAND);
+            }
+        }
+        __syncthreads();
+    }
+}
 
 // ---- OSD-0 walk, one warp per unconverged shot.  A D-bit vector is spread over the lanes: word w lives in
 // slot w / 32 of lane w % 32, so the lowest set bit is one ballot per slot.  Basis vectors and their
@@ -488,11 +672,16 @@ int gq_bp_create(gq_dec *dec) {
     GQ_CUDA(cudaMemcpy(dec->d_prior, prior.data(), (size_t)M * 4, cudaMemcpyHostToDevice));
     dec->bp_msgs_per_block = ((size_t)nnz + M + 31) & ~(size_t)31;
     size_t bytes = dec->bp_msgs_per_block * 4;
-    if (bytes <= 192 * 1024) {
+    if (bytes <= 192 * 1024 && !dec->params.bp_scratch) {
         dec->bp_blocks = dem->num_sms * std::max<int>(1, std::min<int>(8, (int)(192 * 1024 / bytes)));
         if (cudaFuncSetAttribute(bp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) GQ_FAIL(GQ_E_CUDA, "BP decoder: cudaFuncSetAttribute failed");   // + 19 KB static (OSD selection)
     } else {
-        dec->bp_blocks = dem->num_sms * 5;   // 48 registers: five blocks of 256 threads per SM
+        // shot-interleaved kernel: BP_BATCH shots per block, c2v[nnz][BP_BATCH] then tot[M][BP_BATCH]
+        dec->bp_msgs_per_block = (size_t)BP_BATCH * ((size_t)nnz + M) + 32;
+        bytes = dec->bp_msgs_per_block * 4;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bp_batched_kernel<BP_BATCH>, 256, (size_t)BP_BATCH * dem->DW * 4) != cudaSuccess || per_sm < 1) per_sm = 2;
+        dec->bp_blocks = dem->num_sms * per_sm;
         GQ_CUDA(cudaMalloc((void **)&dec->d_bp_msgs, bytes * dec->bp_blocks));
     }
     return GQ_OK;
@@ -538,8 +727,13 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
         a.corr_out = corr_out ? corr_out + s0 * a.MW : nullptr;
         a.nshots = ns;
         if (osd) GQ_CUDA(cudaMemsetAsync(dec->d_osd_fail, 0, 8, dem->stream));
-        int blocks = (int)std::min<uint64_t>(ns, (uint64_t)dec->bp_blocks);
-        bp_kernel<<<blocks, 256, smem, dem->stream>>>(a);
+        if (a.use_shared) {
+            int blocks = (int)std::min<uint64_t>(ns, (uint64_t)dec->bp_blocks);
+            bp_kernel<<<blocks, 256, smem, dem->stream>>>(a);
+        } else {
+            int blocks = (int)std::min<uint64_t>((ns + BP_BATCH - 1) / BP_BATCH, (uint64_t)dec->bp_blocks);
+            bp_batched_kernel<BP_BATCH><<<blocks, 256, (size_t)BP_BATCH * dem->DW * 4, dem->stream>>>(a);
+        }
         GQ_CUDA(cudaGetLastError());
         ++*launches;
         if (!osd) continue;

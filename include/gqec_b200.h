@@ -52,7 +52,9 @@ typedef struct gq_decoder_params {
     int32_t legacy_tiers;      /* matching: 1 = skip the first tier (A/B testing only) */
     int32_t bp_osd;            /* BP: 1 = order-0 ordered-statistics decoding (OSD-0) of the shots BP leaves
                                   unconverged -- the "OSD" of the reference's decoder="bposd" (stimbposd) */
-    int32_t reserved[6];
+    int32_t bp_scratch;        /* BP: 1 = use the global-scratch (shot-interleaved) kernel even when the messages would fit
+                                  shared memory (tests) */
+    int32_t reserved[5];
 } gq_decoder_params;
 
 typedef struct gq_dem_info {

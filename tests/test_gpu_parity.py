@@ -402,10 +402,13 @@ def _bp_case(name, **params):
     return dem, demh, be.DecoderHandle(demh, be.BP_MINSUM, **params)
 
 
-@pytest.mark.parametrize("name,nshots", [("rot3", 300), ("steane", 300), ("rot5", 120)])
-def test_bp_matches_oracle_bit_for_bit(name, nshots):
-    """Same schedule, same fp32 summation order as oracle/bp_oracle.c: identical decisions and iteration counts."""
-    dem, demh, bp = _bp_case(name, bp_max_iter=25, bp_alpha=0.9)
+@pytest.mark.parametrize("name,nshots,scratch", [("rot3", 300, False), ("steane", 300, False), ("rot5", 120, False),
+                                                 ("rot3", 301, True), ("rot5", 123, True), ("toric4", 77, True)])
+def test_bp_matches_oracle_bit_for_bit(name, nshots, scratch):
+    """Same schedule, same fp32 summation order as oracle/bp_oracle.c: identical decisions and iteration counts -- for the
+    one-shot-per-block kernel (messages in shared memory) and for the shot-interleaved kernel of the big models
+    (bp_scratch forces it here; ragged shot counts leave its last group of eight partly empty)."""
+    dem, demh, bp = _bp_case(name, bp_max_iter=25, bp_alpha=0.9, bp_scratch=scratch)
     orc = po.BpOracle(dem, max_iter=25, alpha=0.9)
     dets, obs = demh.sample(17, 0, nshots)
     pred, iters, flags, corr = bp.decode(dets, want_weights=True, want_flags=True, want_corrections=True)
@@ -427,12 +430,13 @@ def test_bp_matches_oracle_bit_for_bit(name, nshots):
     assert nconv > 0.5 * nshots
 
 
-@pytest.mark.parametrize("name,nshots,iters", [("rot3", 400, 4), ("steane", 400, 3), ("rot5", 150, 6), ("toric4", 150, 8)])
-def test_bp_osd_matches_oracle_bit_for_bit(name, nshots, iters):
+@pytest.mark.parametrize("name,nshots,iters,scratch", [("rot3", 400, 4, False), ("steane", 400, 3, False), ("rot5", 150, 6, False),
+                                                       ("toric4", 150, 8, False), ("steane", 403, 3, True), ("rot5", 149, 6, True)])
+def test_bp_osd_matches_oracle_bit_for_bit(name, nshots, iters, scratch):
     """BP (few iterations, so that many shots stay unconverged) + OSD-0: the same error vector as
     oracle/bp_oracle.c::orc_bp_osd0 on every shot, and every solved shot reproduces its syndrome."""
     dem, demh, _ = case(name)
-    bp = be.DecoderHandle(demh, be.BP_MINSUM, bp_max_iter=iters, bp_alpha=0.9, bp_osd=True)
+    bp = be.DecoderHandle(demh, be.BP_MINSUM, bp_max_iter=iters, bp_alpha=0.9, bp_osd=True, bp_scratch=scratch)
     orc = po.BpOracle(dem, max_iter=iters, alpha=0.9)
     dets, obs = demh.sample(23, 0, nshots)
     pred, it_gpu, flags, corr = bp.decode(dets, want_weights=True, want_flags=True, want_corrections=True)
