@@ -103,7 +103,7 @@ extern "C" int gq_decoder_create(gq_dem *dem, int kind, const gq_decoder_params 
     dec->kind = kind;
     default_params(&dec->params);
     if (params) {
-        if (params->weight_levels > 0) dec->params.weight_levels = params->weight_levels;
+        if (params->weight_levels > 0) { dec->params.weight_levels = params->weight_levels; dec->weight_levels_auto = false; }
         dec->params.fast_capacity = params->fast_capacity;
         dec->params.with_corrections = params->with_corrections;
         dec->params.legacy_tiers = params->legacy_tiers;

@@ -79,6 +79,7 @@ struct gq_dec {
     std::vector<uint64_t> eobs;
     std::vector<double> eprob;
     uint32_t fast_cap = 0, max_cap = 0, max_dist = 0;
+    bool weight_levels_auto = true;    // the caller left weight_levels at its default (the decoder may coarsen the grid)
     bool big_classes = false;          // first-tier classes K = 48, 64 (1025 .. 2048 defects) usable: max_dist < 2^15
     uint16_t *d_dist = nullptr;        // [D][D+1]
     uint8_t *d_pobs = nullptr;         // [D][D+1] observable mask of the shortest path

@@ -653,10 +653,20 @@ int gq_matching_create(gq_dec *dec) {
         if (kv.first.second == GQ_NO_DET) dec->num_boundary++;
     }
     dec->num_edges = (uint32_t)dec->eu.size();
-    for (double w : wf) {
-        double v = wmax > 0 ? rint(w * (levels / wmax)) : 1.0;
-        dec->ew.push_back((uint32_t)std::max(1.0, v));
-    }
+    auto set_weights = [&](int lv) {   // the heaviest edge maps to lv
+        dec->ew.clear();
+        for (double w : wf) {
+            double v = wmax > 0 ? rint(w * (lv / wmax)) : 1.0;
+            dec->ew.push_back((uint32_t)std::max(1.0, v));
+        }
+    };
+    set_weights(levels);
+    // expected defect count from the DEM (capacities below; and whether the 1025 .. 2048-defect classes matter)
+    std::vector<double> keep(D, 1.0);
+    for (uint32_t m = 0; m < dem->M; ++m)
+        for (uint32_t q = dem->det_indptr[m]; q < dem->det_indptr[m + 1]; ++q) keep[dem->det_idx[q]] *= 1 - 2 * dem->p[m];
+    double mu = 0;
+    for (uint32_t d = 0; d < D; ++d) mu += 0.5 * (1 - keep[d]);
     // ---- adjacency (node D = boundary)
     std::vector<uint32_t> adj_ptr(N + 1, 0);
     for (uint32_t e = 0; e < dec->num_edges; ++e) {
@@ -725,7 +735,11 @@ int gq_matching_create(gq_dec *dec) {
             row_max[s] = mx;
         }
     };
-    {
+    auto run_apsp = [&]() {
+        std::fill(dist.begin(), dist.end(), (uint16_t)0xFFFFu);
+        std::fill(pobs.begin(), pobs.end(), (uint8_t)0);
+        if (want_next) std::fill(nexttab.begin(), nexttab.end(), (uint16_t)0xFFFFu);
+        std::fill(row_max.begin(), row_max.end(), 0u);
         unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
         nt = std::min<unsigned>(nt, N);
         std::vector<std::thread> th;
@@ -735,10 +749,21 @@ int gq_matching_create(gq_dec *dec) {
             if (b < e) th.emplace_back(worker, b, e);
         }
         for (auto &t : th) t.join();
+        dec->max_dist = *std::max_element(row_max.begin(), row_max.end());
+    };
+    run_apsp();
+    // The 1025 .. 2048-defect classes of the first tier keep event times in 18 bits, which holds when the longest shortest
+    // path is below 2^15.  A model that will produce such shots (mean + 6 sigma defects > 1024: d >= 20 codes) and whose
+    // paths are a little longer -- unrotated d = 23 at low p: 33 k at 1000 levels -- gets a proportionally coarser weight
+    // grid (>= 900 levels: the grid moves 4 predictions per million at 1000 levels) instead of
+    // sending those shots to the memory-resident tier, which is two orders of magnitude slower.
+    if (!too_far && dec->max_dist >= 32768u && dec->max_dist < 36000u && mu + 6 * sqrt(2 * mu + 1) > 1024 && dec->weight_levels_auto) {
+        levels = (int)((double)levels * 32700.0 / dec->max_dist);
+        set_weights(levels);
+        run_apsp();
     }
     if (too_far) GQ_FAIL(GQ_E_UNSUPPORTED, "matching decoder: path lengths exceed 16 bits; lower weight_levels");
     for (uint32_t s = 0; s < N; ++s) dist[(size_t)s * NT + s] = 0xFFFFu;   // no self pairs (match_tree.cuh relies on it)
-    dec->max_dist = *std::max_element(row_max.begin(), row_max.end());
     dec->big_classes = dec->max_dist < 32768u;   // event times (<= 8 x a table distance) fit the 18 bits an 11-bit vertex field leaves
     // ---- the NBR_LEN nearest other detectors of every detector (ascending distance, ties by index) for the
     // first tier's dual start; rows D and D + 1 and the tails are padding (see match_tree.cuh)
@@ -766,12 +791,7 @@ int gq_matching_create(gq_dec *dec) {
         }
         for (auto &t : th) t.join();
     }
-    // ---- capacities: expected defect count from the DEM
-    std::vector<double> keep(D, 1.0);
-    for (uint32_t m = 0; m < dem->M; ++m)
-        for (uint32_t q = dem->det_indptr[m]; q < dem->det_indptr[m + 1]; ++q) keep[dem->det_idx[q]] *= 1 - 2 * dem->p[m];
-    double mu = 0;
-    for (uint32_t d = 0; d < D; ++d) mu += 0.5 * (1 - keep[d]);
+    // ---- capacities
     int fast = dec->params.fast_capacity > 0 ? dec->params.fast_capacity : (int)(mu + 6 * sqrt(2 * mu + 1) + 8);
     fast = std::min<int>(even_up(fast + 1), even_up((int)D + 1));
     fast = std::max(fast, 4);
@@ -926,6 +946,7 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
                 dec->recs_bytes = rec_total + rec_total / 8;
             }
             int nside = 0;
+            bool timed = false;   // the dominant class's kernels ran (its events were recorded)
             for (int oi = 0; oi < MT_CLASSES; ++oi) {
                 const int c = order[oi];
                 if (counts[c] == 0) continue;
@@ -957,6 +978,7 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
                 default: lrc = launch_tree_class<64>(b, d_counts + 16 + c, dem, st, launches, c == dom ? dec->kev0 : nullptr, c == dom ? dec->kev1 : nullptr); break;
                 }
                 if (lrc) GQ_FAIL(lrc, "matching decoder: first-tier kernel launch failed");
+                if (c == dom) timed = true;
                 if (st != dem->stream) {
                     GQ_CUDA(cudaEventRecord(dec->side_done[nside - 1], st));
                     GQ_CUDA(cudaStreamWaitEvent(dem->stream, dec->side_done[nside - 1], 0));
@@ -965,7 +987,7 @@ int gq_matching_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, ui
             uint32_t ovf[2];
             GQ_CUDA(cudaMemcpyAsync(ovf, ovf_buf[cur], 8, cudaMemcpyDeviceToHost, dem->stream));
             GQ_CUDA(cudaStreamSynchronize(dem->stream));
-            if (counts[dom]) {
+            if (counts[dom] && timed) {
                 float ms = 0;
                 cudaEventElapsedTime(&ms, dec->kev0, dec->kev1);
                 dec->kprof[0] += ms; dec->kprof[1] += 1; dec->kprof[2] += counts[dom]; dec->kprof[3] = dom < 8 ? dom + 1 : (dom == 8 ? 10 : (dom == 9 ? 12 : (dom == 10 ? 16 : (dom == 11 ? 24 : (dom == 12 ? 32 : (dom == 13 ? 48 : 64))))));

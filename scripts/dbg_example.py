@@ -3,9 +3,11 @@ sys.path.insert(0, '/root/repo')
 import numpy as np
 import graphqec_b200 as gq
 from graphqec_b200 import backend as be
-for code_name in ("RotatedSurfaceCode", "UnrotatedSurfaceCode"):
-    for d in (17, 20, 23):
-        for p in (0.004, 0.006, 0.008, 0.01):
+import itertools
+POINTS = [("UnrotatedSurfaceCode", 23, 0.004), ("UnrotatedSurfaceCode", 23, 0.005), ("RotatedSurfaceCode", 23, 0.01), ("UnrotatedSurfaceCode", 20, 0.007)]
+for code_name, d, p in POINTS:
+    for _ in (0,):
+        for _ in (0,):
             t0 = time.time()
             try:
                 code = getattr(gq, code_name)(distance=d, depolarize1_rate=p, depolarize2_rate=p)

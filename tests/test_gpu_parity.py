@@ -376,15 +376,15 @@ def test_logical_error_rates_inside_oracle_wilson_intervals(golden_dir):
             dem = code.memory_circuit.detector_error_model()
         demh = be.DemHandle(dem, device=0)
         dech = be.DecoderHandle(demh, be.MATCHING)
-        n = -(-fx["shots"] // demh.tile_shots) * demh.tile_shots
+        # the GPU draws many more shots than the fixture holds (16 x, at least 2^22), so that its own sampling noise is a
+        # quarter of the oracle's: its estimate must lie inside the oracle's 95 % interval widened by that remainder
+        n = max(1 << 22, 16 * fx["shots"])
+        n = -(-n // demh.tile_shots) * demh.tile_shots
         shots, errors, _ = dech.collect(20261019, 0, n, 0)
         lo, hi = fx["wilson95"]
         glo, ghi = po.wilson(errors, shots)
-        # the GPU estimate has its own sampling noise: require the two 95 % intervals to overlap
-        # and the GPU point estimate to sit within the oracle interval widened by the GPU's own
-        assert glo <= hi and lo <= ghi, (fx["code"], fx["kwargs"], fx["p"], errors / shots, lo, hi)
         width = (ghi - glo) / 2
-        assert lo - width <= errors / shots <= hi + width
+        assert lo - width <= errors / shots <= hi + width, (fx["code"], fx["kwargs"], fx["p"], errors / shots, lo, hi)
         dech.close(); demh.close()
 
 
