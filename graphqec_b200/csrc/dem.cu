@@ -87,8 +87,12 @@ __global__ void __launch_bounds__(256) sample_kernel(SampleArgs a) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (done) break;
-                    // v uniform in (0, 1): gap = floor(log(1 - v) / log(1 - p))
-                    float v = ((float)rv[k] + 0.5f) * 2.3283064365386963e-10f;
+                    // v uniform in (0, 1): gap = floor(log(1 - v) / log(1 - p)).  (float)rv rounds to 24 bits, so the top 128
+                    // values of rv would give v == 1 and an infinite gap: clamped to the largest float below 1 (gap 16.6 / p,
+                    // beyond every segment).  For v >= 1/2 the rounding moves 1 - v by up to 3e-8: a far hit (gap ~ 9 / p) can
+                    // land a few positions off, symmetrically -- no bias on rates (tests: per-class z-scores, detector marginals;
+                    // LER against the oracle's double-precision sampler at 1.3e8 shots, profiles/r02_ler_samplers.log).
+                    float v = fminf(((float)rv[k] + 0.5f) * 2.3283064365386963e-10f, 0.99999994f);
                     float g = floorf(log1pf(-v) * c.inv_log1m);
                     float room = (float)(end - pos);
                     if (!(g < room)) { done = true; break; }
