@@ -34,11 +34,11 @@ SEED = 20261019
 WORKLOAD = "RotatedSurfaceCode d=11 r=11 p=0.005 Z-memory (BASELINE configs[1], north-star point)"
 ALG_BYTES_PER_SHOT = (1320 + 1) / 8.0   # bit-packed syndrome + observable per shot
 # from the committed ncu --set full capture of the dominant kernel (profiles/, this round); None = not captured
-# profiles/r02_tree_solve_kernel3_v1_summary.txt: 464.9 MB read + 7.5 MB written / 767 034 shots (the hand-off
-# records are ~6 B per defect + 16 B of that), 3.465e9 warp-instructions, 75.2 % of issue slots active
-NCU_DRAM_BYTES_PER_SHOT = (464.897792e6 + 7.536128e6) / 767034
-NCU_WARP_INSTR_PER_SHOT = 3465442451 / 767034
-NCU_ISSUE_ACTIVE_PCT = 75.2
+# profiles/r02_tree_solve_kernel3_summary.txt: 465.7 MB read + 7.6 MB written / 766 327 shots (the hand-off
+# records are ~6 B per defect + 16 B of that), 3.216e9 warp-instructions, 75.0 % of issue slots active
+NCU_DRAM_BYTES_PER_SHOT = (465.733376e6 + 7.633920e6) / 766327
+NCU_WARP_INSTR_PER_SHOT = 3215855058 / 766327
+NCU_ISSUE_ACTIVE_PCT = 75.0
 # both arms print this object verbatim (the driver compares it); run-dependent numbers live under "run"
 CONFIG = {"workload": WORKLOAD, "code": "RotatedSurfaceCode", "distance": 11, "rounds": 11, "p": 0.005, "logic_check": "Z",
           "decoder": "exact minimum-weight perfect matching"}
@@ -345,7 +345,7 @@ def main():
                 # classification), bit-packed syndrome + observable written once
                 "sampler": {"kernel": "sample_kernel (K1+K2)", "achieved": samp_gbs, "frac": samp_gbs / peak, "unit": "GB/s",
                             "shots_per_s": shots / max(samp_ms / max(1, args.steps) * 1e-3, 1e-12),
-                            "bound_note": "Philox + log1pf + shared-memory atomicXor issue, not HBM (profiles/r02_sample_kernel_v1_summary.txt)"},
+                            "bound_note": "Philox + log1pf + shared-memory atomicXor issue, not HBM (profiles/r02_sample_kernel_summary.txt)"},
                 "whole_step": {"achieved": ALG_BYTES_PER_SHOT * shots / max(dev_ms / max(1, args.steps) * 1e-3, 1e-12) / 1e9,
                                "frac": ALG_BYTES_PER_SHOT * shots / max(dev_ms / max(1, args.steps) * 1e-3, 1e-12) / 1e9 / peak},
                 "traffic": NCU_DRAM_BYTES_PER_SHOT * shots_per_launch if NCU_DRAM_BYTES_PER_SHOT else None,
