@@ -266,7 +266,7 @@ class DecoderHandle:
 
     def __init__(self, demh: DemHandle, kind: int = MATCHING, weight_levels: int = 0, fast_capacity: int = 0,
                  with_corrections: bool = False, bp_max_iter: int = 0, bp_alpha: float = 0.0,
-                 legacy_tiers: bool = False, bp_osd: bool = False, bp_scratch: bool = False) -> None:
+                 legacy_tiers: bool = False, bp_osd: bool = False, bp_scratch: int = 0) -> None:
         lib = load_library()
         self.demh = demh
         self.kind = kind
@@ -277,7 +277,7 @@ class DecoderHandle:
         p.bp_max_iter, p.bp_alpha = int(bp_max_iter), float(bp_alpha)
         p.legacy_tiers = int(bool(legacy_tiers))
         p.bp_osd = int(bool(bp_osd))
-        p.bp_scratch = int(bool(bp_scratch))
+        p.bp_scratch = int(bp_scratch)      # 0 auto, 1 global-scratch kernel, 2 compressed min-sum kernel
         _check(lib.gq_decoder_create(demh._h, kind, ctypes.byref(p), ctypes.byref(self._h)), "gq_decoder_create")
         gi = _GraphInfo()
         _check(lib.gq_decoder_get_graph_info(self._h, ctypes.byref(gi)), "gq_decoder_get_graph_info")

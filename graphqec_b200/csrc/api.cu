@@ -110,7 +110,7 @@ extern "C" int gq_decoder_create(gq_dem *dem, int kind, const gq_decoder_params 
         if (params->bp_max_iter > 0) dec->params.bp_max_iter = params->bp_max_iter;
         if (params->bp_alpha > 0) dec->params.bp_alpha = params->bp_alpha;
         dec->params.bp_osd = params->bp_osd ? 1 : 0;
-        dec->params.bp_scratch = params->bp_scratch ? 1 : 0;
+        dec->params.bp_scratch = params->bp_scratch;
     }
     int rc;
     if (kind == GQ_DECODER_MATCHING) rc = gq_matching_create(dec);

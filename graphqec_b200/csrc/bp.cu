@@ -29,6 +29,7 @@
 //    shots) rest is counted and reported as sinter's "discards".  Identical to oracle/bp_oracle.c::orc_osd0
 //    with max_candidates = -osd_k.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -71,21 +72,21 @@ __device__ __forceinline__ uint32_t osd_key(float x) {   // order-preserving map
 }
 
 // The k variables with the smallest posterior, ascending (ties by index), written to out[0..k); k <= OSD_NCAND.
-// All 256 threads of the block call it; tot[] holds the block's M posteriors.
-__device__ void osd_select(const float *tot, uint32_t stride, uint32_t M, uint32_t k, uint32_t *out) {
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_prefix, s_rank;
-    __shared__ uint32_t cnt_less[256], cnt_tie[256];
-    __shared__ unsigned long long pairs[OSD_NCAND];
-    __shared__ uint32_t s_fill;
-    const int tid = threadIdx.x;
+// All threads of the block (>= 256) call it; tot[] holds the block's M posteriors.
+// ws: OSD_WS_WORDS 8-byte words of shared memory (the callers that have nothing to spare declare it statically).
+static constexpr int OSD_WS_WORDS = OSD_NCAND + 3 * 128 + 2;
+__device__ void osd_select(const float *tot, uint32_t stride, uint32_t M, uint32_t k, uint32_t *out, unsigned long long *ws) {
+    unsigned long long *pairs = ws;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(ws + OSD_NCAND), *cnt_less = hist + 256, *cnt_tie = hist + 512;
+    uint32_t &s_prefix = hist[768], &s_rank = hist[769], &s_fill = hist[770];
+    const int tid = threadIdx.x, nt = blockDim.x;     // nt >= 256; the chunked compaction is done by the first 256 threads
     if (k > M) k = M;
     // ---- k-th smallest key by 8-bit digits, most significant first
     uint32_t prefix = 0, mask = 0, rank = k;        // rank: 1-based rank still to find inside the prefix group
     for (int shift = 24; shift >= 0; shift -= 8) {
-        hist[tid] = 0;
+        if (tid < 256) hist[tid] = 0;
         __syncthreads();
-        for (uint32_t v = tid; v < M; v += 256) {
+        for (uint32_t v = tid; v < M; v += nt) {
             const uint32_t key = osd_key(tot[(size_t)v * stride]);
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
@@ -101,16 +102,16 @@ __device__ void osd_select(const float *tot, uint32_t stride, uint32_t M, uint32
         __syncthreads();
     }
     const uint32_t kth = prefix, need_ties = rank;   // keys < kth all belong; of the keys == kth the first need_ties by index
-    // ---- index-ordered compaction: thread t owns the contiguous chunk [t * C, (t + 1) * C)
-    const uint32_t C = (M + 255) / 256, lo = tid * C, hi = min(M, lo + C);
-    uint32_t nl = 0, nt = 0;
-    for (uint32_t v = lo; v < hi; ++v) { const uint32_t key = osd_key(tot[(size_t)v * stride]); nl += key < kth; nt += key == kth; }
-    cnt_less[tid] = nl; cnt_tie[tid] = nt;
+    // ---- index-ordered compaction: thread t < 256 owns the contiguous chunk [t * C, (t + 1) * C)
+    const uint32_t C = (M + 255) / 256, lo = min(M, tid * C), hi = tid < 256 ? min(M, lo + C) : lo;
+    uint32_t nl = 0, nt_ = 0;
+    for (uint32_t v = lo; v < hi; ++v) { const uint32_t key = osd_key(tot[(size_t)v * stride]); nl += key < kth; nt_ += key == kth; }
+    if (tid < 256) { cnt_less[tid] = nl; cnt_tie[tid] = nt_; }
     if (tid == 0) s_fill = 0;
-    for (uint32_t i = tid; i < OSD_NCAND; i += 256) pairs[i] = ~0ull;
+    for (uint32_t i = tid; i < OSD_NCAND; i += nt) pairs[i] = ~0ull;
     __syncthreads();
     uint32_t tie_before = 0;
-    for (int t = 0; t < tid; ++t) tie_before += cnt_tie[t];
+    for (int t = 0; t < tid && t < 256; ++t) tie_before += cnt_tie[t];
     for (uint32_t v = lo; v < hi; ++v) {
         const uint32_t key = osd_key(tot[(size_t)v * stride]);
         bool take = key < kth;
@@ -121,7 +122,7 @@ __device__ void osd_select(const float *tot, uint32_t stride, uint32_t M, uint32
     // ---- bitonic sort of the (key, index) pairs (padding sorts last)
     for (uint32_t size = 2; size <= OSD_NCAND; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t i = tid; i < OSD_NCAND / 2; i += 256) {
+            for (uint32_t i = tid; i < OSD_NCAND / 2; i += nt) {
                 const uint32_t a = 2 * i - (i & (stride - 1)), b = a + stride;
                 const bool up = (a & size) == 0;
                 const unsigned long long x = pairs[a], y = pairs[b];
@@ -130,7 +131,7 @@ __device__ void osd_select(const float *tot, uint32_t stride, uint32_t M, uint32
             __syncthreads();
         }
     }
-    for (uint32_t i = tid; i < OSD_NCAND; i += 256) out[i] = i < k ? (uint32_t)pairs[i] : 0xFFFFFFFFu;
+    for (uint32_t i = tid; i < OSD_NCAND; i += nt) out[i] = i < k ? (uint32_t)pairs[i] : 0xFFFFFFFFu;
     __syncthreads();
 }
 
@@ -288,7 +289,8 @@ __global__ void __launch_bounds__(256) bp_kernel(BpArgs a) {
             __shared__ uint32_t s_slot;
             if (tid == 0) { s_slot = atomicAdd(a.fail_count, 1u); a.fail_list[s_slot] = (uint32_t)shot; }
             __syncthreads();
-            osd_select(tot, 1u, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_NCAND);
+            __shared__ unsigned long long osd_ws[OSD_WS_WORDS];
+            osd_select(tot, 1u, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_NCAND, osd_ws);
         }
     }
 }
@@ -470,17 +472,223 @@ __global__ void __launch_bounds__(256) bp_batched_kernel(BpArgs a) {
             if (a.osd_k) {
                 if (tid == 0) { s_slot = atomicAdd(a.fail_count, 1u); a.fail_list[s_slot] = (uint32_t)(shot0 + sh); }
                 __syncthreads();
-                osd_select(tot + sh, (uint32_t)S, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_NCAND);
+                __shared__ unsigned long long osd_ws[OSD_WS_WORDS];
+                osd_select(tot + sh, (uint32_t)S, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_NCAND, osd_ws);
             }
         }
         __syncthreads();
     }
 }
 
+// ---- compressed min-sum ("cms"): the same flooding schedule with NO per-edge message in memory.
+// A min-sum check-to-variable message takes one of two magnitudes: c2v(c, v) = alpha * sign * (v == argmin_c ? min2_c : min1_c).
+// So a check is fully described by {min1, argmin, min2, sign product} (12 bytes) plus ONE BIT per edge (the sign of the
+// variable-to-check message it was computed from), and a posterior is a sum a variable re-forms from the <= 16 records of
+// its checks.  One block = one shot, everything in shared memory (BB-144 x 12 rounds: 100 KB, against 1.8 MB of fp32
+// messages per shot in the kernels above), and the passes turn inside out: instead of a check gathering the posteriors of
+// its ~230 variables (a 4-byte gather per edge from a per-shot array that only HBM / L2 can hold), a VARIABLE reads the
+// records of its checks, forms its posterior and its variable-to-check messages in registers, and offers each message to
+// the check's next record with shared-memory atomics: min1/argmin = 64-bit atomicMin of (|m| bits << 32 | variable), min2
+// = atomicMin of whatever loses or is displaced at min1, sign product and decision parity = atomicXor.  A message at or
+// above the record's current min2 cannot change it and is filtered by a plain load first, so only a few of a check's
+// ~230 offers reach an atomic.  The only global traffic is the Tanner graph itself (coalesced, L2-resident, shared by all
+// blocks).  Same fp32 operations in the same order as oracle/bp_oracle.c (the sum over a variable's checks in ascending
+// check order, argmin ties to the lowest variable -- immaterial, min2 == min1 then): bit-identical decisions and
+// iteration counts.
+// Variables are processed in tiles of 32 with equal degree (sorted by degree at set-up, a permutation: tie rules use the
+// original index), so the per-degree bodies are straight-line code over registers.
+struct CmsArgs {
+    const uint32_t *dets;
+    uint32_t *pred;
+    int32_t *iters_out;
+    uint8_t *flags_out;
+    uint32_t *corr_out;
+    uint64_t nshots;
+    uint32_t D, M, DW, OW, MW;
+    uint32_t ntiles, FW, SW;           // tiles of 32 variables; words of packed check flags; words of edge sign bits
+    uint32_t grp_tile[18];             // tiles of degree g: [grp_tile[g], grp_tile[g + 1]) (tiles are sorted by degree)
+    uint32_t grp_word[17];             // first sign word of degree g's first tile; tile t of the group starts g * (t - first) words later,
+                                       // and its checks at 32 * that
+    const uint32_t *tile_var;          // [ntiles * 32] original variable index (M: padding lane)
+    const float *tile_prior;           // [ntiles * 32]
+    const uint32_t *tile_obs;          // [ntiles * 32] observable mask
+    const uint16_t *tile_chk;          // [32 * SW] check of edge j of lane l of a tile at 32 * (first word + j) + l
+    int max_iter;
+    float alpha;
+    uint32_t *cursor;                  // next shot to claim
+    float *post;                       // per block: M posteriors of an unconverged shot, for the OSD candidate selection
+    uint32_t osd_k;
+    uint32_t *cand, *fail_list, *fail_count;
+};
+
+static constexpr unsigned long long CMS_INFKEY = 0x7f800000ffffffffull;
+
+// Records of check c: key1[buffer][c] = (min1 bits << 32) | argmin variable (bit 31 of the low word, once the record
+// is closed: the total sign), key2[buffer][c] = min2 bits (8- and 4-byte strides: an interleaved 16-byte layout doubled the
+// shared-memory bank conflicts of the random record reads, measured).  Check D is a dummy whose closed record always reads zero:
+// the padding lanes of a tile (variable index M, prior 1e30) point at it, so the tile bodies carry no "valid lane" tests.
+template <int DG, bool POST>
+__device__ __forceinline__ void cms_group(const CmsArgs &a, int lane, int wid, int nw, const unsigned long long *key1o,
+                                          const uint32_t *key2o, unsigned long long *key1n, uint32_t *key2n, uint32_t *flagsn,
+                                          uint32_t *sgn, uint32_t *decw, float *post) {
+    const uint32_t t0 = a.grp_tile[DG], t1 = a.grp_tile[DG + 1], w0 = a.grp_word[DG];
+    const uint32_t lsh = 31u - (uint32_t)lane;
+    for (uint32_t t = t0 + wid; t < t1; t += nw) {
+        const uint32_t slot = t * 32u + lane, wbase = w0 + (t - t0) * DG;
+        const uint32_t v = a.tile_var[slot];
+        float tot = a.tile_prior[slot];
+        uint32_t c[DG > 0 ? DG : 1];
+        float cv[DG > 0 ? DG : 1];
+        const uint16_t *cp = a.tile_chk + (size_t)wbase * 32u + lane;
+        uint32_t *sp = sgn + wbase;
+#pragma unroll
+        for (int j = 0; j < DG; ++j) c[j] = cp[j * 32];
+#pragma unroll
+        for (int j = 0; j < DG; ++j) {
+            const unsigned long long k1 = key1o[c[j]];
+            const uint32_t lo = (uint32_t)k1;
+            uint32_t mag = (uint32_t)(k1 >> 32);
+            if ((lo & 0x7fffffffu) == v) mag = key2o[c[j]];
+            const uint32_t sg = (lo ^ (sp[j] << lsh)) & 0x80000000u;
+            cv[j] = __fmul_rn(a.alpha, __uint_as_float(mag | sg));
+        }
+#pragma unroll
+        for (int j = 0; j < DG; ++j) tot = __fadd_rn(tot, cv[j]);
+        const bool bit = tot < 0.0f;
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) decw[t] = word;
+        if (POST) post[v] = tot;
+        if (word) {                  // rare: some variable of the tile is decided "error" -- its checks' decision parities flip
+            if (bit) {
+#pragma unroll
+                for (int j = 0; j < DG; ++j) atomicXor(&flagsn[c[j] >> 4], 2u << (2u * (c[j] & 15u)));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DG; ++j) {
+            const float m = __fsub_rn(tot, cv[j]);
+            const bool neg = m < 0.0f;
+            const uint32_t nsg = __ballot_sync(0xffffffffu, neg);
+            if (lane == 0) sp[j] = nsg;
+            const uint32_t cc = c[j];
+            const uint32_t magb = __float_as_uint(m) & 0x7fffffffu;
+            const uint32_t cur2 = key2n[cc];
+            if (neg || magb < cur2) {            // one divergent region per edge for everything that is rare
+                if (neg) atomicXor(&flagsn[cc >> 4], 1u << (2u * (cc & 15u)));
+                if (magb < cur2) {
+                    const unsigned long long key = ((unsigned long long)magb << 32) | v;
+                    const unsigned long long old = atomicMin(&key1n[cc], key);
+                    const uint32_t loser = key < old ? (uint32_t)(old >> 32) : magb;
+                    if (loser < cur2) atomicMin(&key2n[cc], loser);
+                }
+            }
+        }
+    }
+}
+
+// one phase: the degree groups in turn (no barrier between them); the bodies are straight-line code per degree, entered
+// once per group -- a per-tile switch compiled into a chain of indirect branches that cost more than a small tile's work
+template <bool POST>
+__device__ __forceinline__ void cms_phase(const CmsArgs &a, int lane, int wid, int nw, const unsigned long long *key1o, const uint32_t *key2o,
+                                          unsigned long long *key1n, uint32_t *key2n, uint32_t *flagsn, uint32_t *sgn, uint32_t *decw, float *post) {
+#define CMS_GROUP(G) cms_group<G, POST>(a, lane, wid, nw, key1o, key2o, key1n, key2n, flagsn, sgn, decw, post);
+    CMS_GROUP(0) CMS_GROUP(1) CMS_GROUP(2) CMS_GROUP(3) CMS_GROUP(4) CMS_GROUP(5) CMS_GROUP(6) CMS_GROUP(7) CMS_GROUP(8)
+    CMS_GROUP(9) CMS_GROUP(10) CMS_GROUP(11) CMS_GROUP(12) CMS_GROUP(13) CMS_GROUP(14) CMS_GROUP(15) CMS_GROUP(16)
+#undef CMS_GROUP
+}
+
+__global__ void __launch_bounds__(1024, 1) bp_cms_kernel(CmsArgs a) {
+    extern __shared__ unsigned long long cms_smem[];
+    __shared__ uint32_t s_nc[2], s_obs, s_shot, s_slot;
+    const uint32_t D1 = a.D + 1;
+    unsigned long long *key1 = cms_smem;                               // [2][D + 1]
+    uint32_t *key2 = reinterpret_cast<uint32_t *>(key1 + 2 * (size_t)D1);    // [2][D + 1]
+    uint32_t *flags = key2 + 2 * (size_t)D1;                           // [2][FW]  per check: bit 0 sign product, bit 1 decision parity
+    uint32_t *sgn = flags + 2 * (size_t)a.FW;                          // [SW]
+    uint32_t *decw = sgn + a.SW;                                       // [ntiles]
+    uint32_t *syn = decw + a.ntiles;                                   // [DW]
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    float *post_blk = a.post ? a.post + (size_t)blockIdx.x * (a.M + 1) : nullptr;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_shot = atomicAdd(a.cursor, 1u);
+        __syncthreads();
+        const uint64_t shot = s_shot;
+        if (shot >= a.nshots) break;
+        for (uint32_t i = tid; i < D1; i += nt) { key1[i] = 0ull; key1[D1 + i] = CMS_INFKEY; key2[i] = 0u; key2[D1 + i] = 0x7f800000u; }
+        for (uint32_t i = tid; i < 2 * a.FW; i += nt) flags[i] = 0u;
+        for (uint32_t i = tid; i < a.SW; i += nt) sgn[i] = 0u;
+        for (uint32_t i = tid; i < a.DW; i += nt) syn[i] = a.dets[shot * a.DW + i];
+        if (tid == 0) { s_nc[0] = 0; s_nc[1] = 0; s_obs = 0; }
+        __syncthreads();
+        int converged = 0, used = a.max_iter;
+        for (int it = 1; it <= a.max_iter + 1; ++it) {
+            const int o = (it + 1) & 1, n = it & 1;          // old / new record buffers
+            unsigned long long *key1n = key1 + (size_t)n * D1, *key1x = key1 + (size_t)o * D1;
+            uint32_t *key2n = key2 + (size_t)n * D1, *key2x = key2 + (size_t)o * D1, *flagsn = flags + (size_t)n * a.FW;
+            if (a.osd_k && it == a.max_iter + 1) cms_phase<true>(a, lane, wid, nw, key1x, key2x, key1n, key2n, flagsn, sgn, decw, post_blk);
+            else cms_phase<false>(a, lane, wid, nw, key1x, key2x, key1n, key2n, flagsn, sgn, decw, nullptr);
+            __syncthreads();
+            // ---- close the new records: decision parity against the syndrome, total sign into the argmin word; the
+            // old buffer becomes the next phase's new one
+            {
+                uint32_t *flagsx = flags + (size_t)o * a.FW;
+                uint32_t bad = 0;
+                for (uint32_t cc = tid; cc < D1; cc += nt) {
+                    if (cc < a.D) {
+                        const uint32_t f = (flagsn[cc >> 4] >> (2u * (cc & 15u))) & 3u;
+                        const uint32_t sc = (syn[cc >> 5] >> (cc & 31u)) & 1u;
+                        bad |= (f >> 1) ^ sc;
+                        key1n[cc] |= (unsigned long long)((f ^ sc) & 1u) << 31;
+                    } else { key1n[cc] = 0ull; key2n[cc] = 0u; }
+                    key1x[cc] = CMS_INFKEY;
+                    key2x[cc] = 0x7f800000u;
+                }
+                if (bad) s_nc[it & 1] = 1u;
+                if (tid == 0) s_nc[(it + 1) & 1] = 0u;
+                __syncthreads();
+                for (uint32_t i = tid; i < a.FW; i += nt) flagsx[i] = 0u;
+            }
+            const uint32_t notconv = s_nc[it & 1];
+            if (it > 1 && notconv == 0) { converged = 1; used = it - 1; break; }
+            __syncthreads();
+        }
+        // ---- outcome: the decision bits of the last phase
+        uint32_t om = 0;
+        uint32_t *corr_row = a.corr_out ? a.corr_out + shot * a.MW : nullptr;
+        if (corr_row) {
+            for (uint32_t i = tid; i < a.MW; i += nt) corr_row[i] = 0u;
+            __syncthreads();
+        }
+        for (uint32_t t = wid; t < a.ntiles; t += nw) {
+            if ((decw[t] >> lane) & 1u) {
+                om ^= a.tile_obs[t * 32u + lane];
+                if (corr_row) { const uint32_t v = a.tile_var[t * 32u + lane]; atomicOr(&corr_row[v >> 5], 1u << (v & 31u)); }
+            }
+        }
+        om = __reduce_xor_sync(0xffffffffu, om);
+        if (lane == 0 && om) atomicXor(&s_obs, om);
+        __syncthreads();
+        if (tid == 0) {
+            a.pred[shot * a.OW] = s_obs;
+            for (uint32_t w = 1; w < a.OW; ++w) a.pred[shot * a.OW + w] = 0;
+            if (a.iters_out) a.iters_out[shot] = converged ? used : -a.max_iter;
+            if (a.flags_out) a.flags_out[shot] = converged ? 0 : 1;
+        }
+        if (a.osd_k && !converged) {
+            if (tid == 0) { s_slot = atomicAdd(a.fail_count, 1u); a.fail_list[s_slot] = (uint32_t)shot; }
+            __syncthreads();
+            osd_select(post_blk, 1u, a.M, a.osd_k, a.cand + (size_t)s_slot * OSD_NCAND, cms_smem);   // the records are free now
+        }
+    }
+}
+
 // ---- OSD-0 walk, one warp per unconverged shot.  A D-bit vector is spread over the lanes: word w lives in
-// slot w / 32 of lane w % 32, so the lowest set bit is one ballot per slot.  Basis vectors and their
-// coefficient sets (one bit per basis ordinal, 32 ordinals per lane) live in a per-warp HBM/L2 scratch; every
-// lane only ever reads back the words it wrote itself.
+// slot w / 32 of lane w % 32, so the lowest set bit is one ballot per slot.  Basis vectors and, per basis vector, the
+// set of earlier basis vectors that were folded into it (one bit per basis ordinal, 32 ordinals per lane; written once,
+// read once in the final back-substitution) live in a per-warp HBM/L2 scratch; every lane only ever reads back the words
+// it wrote itself.
 struct OsdArgs {
     const uint32_t *dets;
     uint32_t *pred;
@@ -490,6 +698,8 @@ struct OsdArgs {
     uint32_t nfail;
     uint32_t D, DW, OW, MW, M;
     const uint32_t *var_ptr, *var_chk, *var_obs;
+    const uint32_t *chk_ptr, *chk_var;   // rows of H (variables of every detector, ascending): the targeted part of the walk
+    uint32_t *cursor;         // next unconverged shot to claim
     uint32_t *scratch;        // per warp: kmax x (32 WPL basis words + 32 WPL coefficient words) + kmax columns
     size_t scratch_stride;    // words
     uint32_t kmax;            // basis capacity = D (every independent column fits)
@@ -515,12 +725,17 @@ template <int WPL>
 __global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
     extern __shared__ uint16_t piv_all[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint16_t *piv = piv_all + (size_t)wib * ((a.D + 1) & ~1u);
     uint32_t *basis = a.scratch + (size_t)warp * a.scratch_stride;
     uint32_t *coef = basis + (size_t)a.kmax * 32 * WPL;
     uint32_t *col = coef + (size_t)a.kmax * 32 * WPL;
-    for (uint32_t item = warp; item < a.nfail; item += nwarps) {
+    // shots differ by two orders of magnitude in the length of their walk: warps claim the next one with an atomic
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(a.cursor, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= a.nfail) break;
         const uint32_t shot = a.fail_list[item];
         const uint32_t *cand = a.cand + (size_t)item * OSD_NCAND;
         for (uint32_t r = lane; r < a.D; r += 32) piv[r] = 0xFFFFu;
@@ -536,23 +751,52 @@ __global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
         __syncwarp();
         int nb = 0;
         bool done = false;
+        // A reduction step XORs the basis vector whose pivot (lowest set bit) is the vector's lowest set bit r: both are zero
+        // below r, so only the words from r / 32 on are loaded.  A vector never meets the same basis vector twice (later
+        // steps only touch bits above r), so "which basis vectors went into it" is a plain bit set -- one bit set per
+        // step in registers, no second row to load and XOR per step (the kernel is bound by the bytes it moves).
+        auto set_bit = [&](uint32_t (&x)[WPL], uint32_t p) {
+#pragma unroll
+            for (int j = 0; j < WPL; ++j)
+                if ((int)(p >> 10) == j && lane == (int)((p >> 5) & 31u)) x[j] |= 1u << (p & 31u);
+        };
         // reduce the syndrome against the basis; done when nothing is left of it
-        auto reduce_s = [&]() {
+        auto reduce_s = [&]() -> int {       // the lowest bit left of the syndrome (it has no pivot), -1 = nothing left
             for (;;) {
                 const int r = osd_lowbit<WPL>(s, lane);
-                if (r < 0) { done = true; return; }
+                if (r < 0) { done = true; return -1; }
                 const uint32_t p = piv[r];
-                if (p == 0xFFFFu) return;
+                if (p == 0xFFFFu) return r;
+                const uint32_t wr = (uint32_t)r >> 5;
 #pragma unroll
-                for (int j = 0; j < WPL; ++j) { s[j] ^= basis[((size_t)p * WPL + j) * 32 + lane]; sc[j] ^= coef[((size_t)p * WPL + j) * 32 + lane]; }
+                for (int j = 0; j < WPL; ++j)
+                    if ((uint32_t)(j * 32 + lane) >= wr) s[j] ^= basis[((size_t)p * WPL + j) * 32 + lane];
+                set_bit(sc, p);
             }
         };
-        reduce_s();
-        // the reliability-ordered candidates first, then (rare) every variable in index order: the walk ends when the
-        // syndrome is reduced or the basis is complete
-        for (uint32_t i = 0; i < OSD_NCAND + a.M && !done && nb < (int)a.kmax; ++i) {
-            const uint32_t c = i < OSD_NCAND ? cand[i] : i - OSD_NCAND;
-            if (c == 0xFFFFFFFFu) continue;
+        int rs = reduce_s();
+        // The walk: (0) the reliability-ordered candidates; then, for the few shots they do not suffice for, (1) the
+        // variables of the detector that is the lowest bit left of the syndrome, in index order, moving on to the next
+        // such detector whenever that bit changes (a blind walk through all variables spent ~0.7 s of one warp on such a
+        // shot: tens of thousands of dependent columns, each a full reduction chain); (2) if a detector's row is used up
+        // and its bit is still there, every variable in index order.  It ends when the syndrome is reduced or the basis is
+        // complete.  Same schedule as oracle/bp_oracle.c::orc_osd0 with max_candidates < 0.
+        int stage = 0, tr = -1;
+        uint32_t i0 = 0, tk = 0, tend = 0, i2 = 0;
+        while (!done && nb < (int)a.kmax) {
+            uint32_t c;
+            if (stage == 0) {
+                if (i0 >= OSD_NCAND) { stage = 1; continue; }
+                c = cand[i0++];
+                if (c == 0xFFFFFFFFu) continue;
+            } else if (stage == 1) {
+                if (tr != rs) { tr = rs; tk = a.chk_ptr[tr]; tend = a.chk_ptr[tr + 1]; }
+                if (tk >= tend) { stage = 2; continue; }
+                c = a.chk_var[tk++];
+            } else {
+                if (i2 >= a.M) break;
+                c = i2++;
+            }
             uint32_t v[WPL], vc[WPL];
 #pragma unroll
             for (int j = 0; j < WPL; ++j) { v[j] = 0u; vc[j] = 0u; }
@@ -567,20 +811,37 @@ __global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
                 if (r < 0) break;                          // dependent on the basis: skipped
                 const uint32_t p = piv[r];
                 if (p != 0xFFFFu) {
+                    const uint32_t wr = (uint32_t)r >> 5;
 #pragma unroll
-                    for (int j = 0; j < WPL; ++j) { v[j] ^= basis[((size_t)p * WPL + j) * 32 + lane]; vc[j] ^= coef[((size_t)p * WPL + j) * 32 + lane]; }
+                    for (int j = 0; j < WPL; ++j)
+                        if ((uint32_t)(j * 32 + lane) >= wr) v[j] ^= basis[((size_t)p * WPL + j) * 32 + lane];
+                    set_bit(vc, p);
                 } else {
+                    // joins the basis as ordinal nb: the reduced vector, and the set of earlier basis vectors folded into it
 #pragma unroll
                     for (int j = 0; j < WPL; ++j) {
-                        if ((nb >> 10) == j && lane == ((nb >> 5) & 31)) vc[j] |= 1u << (nb & 31);
                         basis[((size_t)nb * WPL + j) * 32 + lane] = v[j];
                         coef[((size_t)nb * WPL + j) * 32 + lane] = vc[j];
                     }
                     if (lane == 0) { piv[r] = (uint16_t)nb; col[nb] = c; }
                     ++nb;
                     __syncwarp();
-                    reduce_s();
+                    rs = reduce_s();
                     break;
+                }
+            }
+        }
+        if (done) {
+            // sc = the basis VECTORS that sum to the syndrome; vector i = column i + the vectors in its set (all of lower
+            // ordinal), so a descending sweep turns it into the basis COLUMNS that sum to the syndrome
+            for (int i = nb - 1; i >= 0; --i) {
+                uint32_t wv = 0;
+#pragma unroll
+                for (int j = 0; j < WPL; ++j) if ((i >> 10) == j) wv = sc[j];
+                const uint32_t word = __shfl_sync(0xffffffffu, wv, (i >> 5) & 31);
+                if ((word >> (i & 31)) & 1u) {
+#pragma unroll
+                    for (int j = 0; j < WPL; ++j) sc[j] ^= coef[((size_t)i * WPL + j) * 32 + lane];
                 }
             }
         }
@@ -672,7 +933,87 @@ int gq_bp_create(gq_dec *dec) {
     GQ_CUDA(cudaMemcpy(dec->d_prior, prior.data(), (size_t)M * 4, cudaMemcpyHostToDevice));
     dec->bp_msgs_per_block = ((size_t)nnz + M + 31) & ~(size_t)31;
     size_t bytes = dec->bp_msgs_per_block * 4;
-    if (bytes <= 192 * 1024 && !dec->params.bp_scratch) {
+    // ---- which kernel: messages in shared memory when the whole model fits (bp_kernel); else the compressed min-sum
+    // kernel when its records fit (bp_cms_kernel); else the shot-interleaved global-scratch kernel.  params.bp_scratch
+    // forces one of the latter two (1 = scratch, 2 = compressed; tests and A/B measurements).
+    const bool small = bytes <= 192 * 1024;
+    if (dec->params.bp_scratch == 2 || (!small && dec->params.bp_scratch == 0)) {
+        uint32_t maxdeg = 0;
+        for (uint32_t m = 0; m < M; ++m) maxdeg = std::max(maxdeg, var_ptr[m + 1] - var_ptr[m]);
+        // variables by degree (stable), every degree group padded to whole tiles of 32
+        std::vector<uint32_t> order(M);
+        for (uint32_t m = 0; m < M; ++m) order[m] = m;
+        // inside a degree group: by check list (lexicographic).  The lanes of a tile then read records of the same or of
+        // neighbouring checks -- same address = broadcast, consecutive records = distinct banks -- where a random order costs
+        // a 3-4-way bank conflict per record read (GQ_CMS_ORDER = 1: by prior LLR, 2: by index; A/B measurements)
+        int order_mode = 0;
+        if (const char *env = getenv("GQ_CMS_ORDER")) order_mode = atoi(env);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            const uint32_t dx = var_ptr[x + 1] - var_ptr[x], dy = var_ptr[y + 1] - var_ptr[y];
+            if (dx != dy) return dx < dy;
+            if (order_mode == 1) return prior[x] < prior[y];
+            if (order_mode == 2) return false;
+            return std::lexicographical_compare(var_chk.begin() + var_ptr[x], var_chk.begin() + var_ptr[x + 1],
+                                                var_chk.begin() + var_ptr[y], var_chk.begin() + var_ptr[y + 1]);
+        });
+        std::vector<uint32_t> desc, tvar, tobs;
+        uint32_t grp_tile[18], grp_word[17];
+        for (int g = 0; g < 18; ++g) grp_tile[g] = 0xFFFFFFFFu;
+        std::vector<float> tprior;
+        std::vector<uint16_t> tchk;
+        uint32_t words = 0;
+        for (size_t i = 0; i < order.size();) {
+            const uint32_t deg = var_ptr[order[i] + 1] - var_ptr[order[i]];
+            size_t j = i;
+            while (j < order.size() && j - i < 32 && var_ptr[order[j] + 1] - var_ptr[order[j]] == deg) ++j;
+            if (deg <= 16 && grp_tile[deg] == 0xFFFFFFFFu) { grp_tile[deg] = (uint32_t)desc.size(); grp_word[deg] = words; }
+            desc.push_back((words << 5) | deg);
+            const size_t e0 = tchk.size();
+            tchk.resize(e0 + (size_t)32 * deg, 0);
+            for (size_t l = 0; l < 32; ++l) {
+                if (i + l < j) {
+                    const uint32_t m = order[i + l];
+                    tvar.push_back(m); tprior.push_back(prior[m]); tobs.push_back(var_obs[m]);
+                    for (uint32_t q = 0; q < deg; ++q) tchk[e0 + (size_t)32 * q + l] = (uint16_t)var_chk[var_ptr[m] + q];
+                } else {      // padding lane: variable M, all edges at the dummy check D, never decided "error"
+                    tvar.push_back(M); tprior.push_back(1e30f); tobs.push_back(0u);
+                    for (uint32_t q = 0; q < deg; ++q) tchk[e0 + (size_t)32 * q + l] = (uint16_t)D;
+                }
+            }
+            words += deg;
+            i = j;
+        }
+        const uint32_t ntiles = (uint32_t)desc.size(), FW = (D + 1 + 15) / 16;
+        grp_tile[17] = ntiles;
+        for (int g = 16; g >= 0; --g) if (grp_tile[g] == 0xFFFFFFFFu) { grp_tile[g] = grp_tile[g + 1]; grp_word[g] = 0; }   // empty group
+        const size_t smem = std::max((size_t)(D + 1) * 24 + ((size_t)2 * FW + words + ntiles + dem->DW) * 4, (size_t)OSD_WS_WORDS * 8);
+        const bool eligible = maxdeg <= 16 && D < 65535 && M < (1u << 31) - 1 && words < (1u << 27) && smem <= 220 * 1024;
+        if (eligible) {
+            dec->cms = true;
+            dec->cms_ntiles = ntiles; dec->cms_FW = FW; dec->cms_SW = words; dec->cms_smem = smem;
+            // two blocks per SM when two sets of records fit (their barriers overlap), else one of 1024 threads
+            const bool two = 2 * (smem + 1024) <= 227 * 1024;
+            dec->cms_threads = two ? 512 : 1024;
+            dec->cms_blocks = dem->num_sms * (two ? 2 : 1);
+            if (const char *env = getenv("GQ_CMS_THREADS")) {      // A/B measurements: threads per block, blocks per SM = 1024 / threads
+                const int t = atoi(env);
+                if ((t == 256 || t == 512 || t == 1024) && (size_t)(1024 / t) * (smem + 1024) <= 227 * 1024) { dec->cms_threads = t; dec->cms_blocks = dem->num_sms * (1024 / t); }
+            }
+            if (cudaFuncSetAttribute(bp_cms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) GQ_FAIL(GQ_E_CUDA, "BP decoder: cudaFuncSetAttribute failed");
+            memcpy(dec->cms_grp_tile, grp_tile, sizeof(grp_tile));
+            memcpy(dec->cms_grp_word, grp_word, sizeof(grp_word));
+            if ((rc = up(&dec->d_cms_var, tvar)) || (rc = up(&dec->d_cms_obs, tobs))) return rc;
+            GQ_CUDA(cudaMalloc((void **)&dec->d_cms_prior, tprior.size() * 4));
+            GQ_CUDA(cudaMemcpy(dec->d_cms_prior, tprior.data(), tprior.size() * 4, cudaMemcpyHostToDevice));
+            GQ_CUDA(cudaMalloc((void **)&dec->d_cms_chk, std::max<size_t>(tchk.size(), 1) * 2));
+            GQ_CUDA(cudaMemcpy(dec->d_cms_chk, tchk.data(), tchk.size() * 2, cudaMemcpyHostToDevice));
+            GQ_CUDA(cudaMalloc((void **)&dec->d_cms_cursor, 4));
+            if (dec->params.bp_osd) GQ_CUDA(cudaMalloc((void **)&dec->d_cms_post, (size_t)dec->cms_blocks * (M + 1) * 4));
+            return GQ_OK;
+        }
+        if (dec->params.bp_scratch == 2) GQ_FAIL(GQ_E_UNSUPPORTED, "BP decoder: the compressed min-sum kernel needs <= 16 detectors per mechanism, <= 65535 detectors and records that fit shared memory");
+    }
+    if (small && !dec->params.bp_scratch) {
         dec->bp_blocks = dem->num_sms * std::max<int>(1, std::min<int>(8, (int)(192 * 1024 / bytes)));
         if (cudaFuncSetAttribute(bp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) GQ_FAIL(GQ_E_CUDA, "BP decoder: cudaFuncSetAttribute failed");   // + 19 KB static (OSD selection)
     } else {
@@ -691,6 +1032,8 @@ void gq_bp_destroy(gq_dec *dec) {
     cudaFree(dec->d_chk_ptr); cudaFree(dec->d_chk_var); cudaFree(dec->d_var_ptr);
     cudaFree(dec->d_var_edge); cudaFree(dec->d_var_obs); cudaFree(dec->d_prior); cudaFree(dec->d_bp_msgs);
     cudaFree(dec->d_var_chk); cudaFree(dec->d_osd_cand); cudaFree(dec->d_osd_fail); cudaFree(dec->d_osd_scratch);
+    cudaFree(dec->d_cms_var); cudaFree(dec->d_cms_obs); cudaFree(dec->d_cms_cursor);
+    cudaFree(dec->d_cms_prior); cudaFree(dec->d_cms_post); cudaFree(dec->d_cms_chk);
 }
 
 int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t *pred_sm,
@@ -703,21 +1046,23 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
     a.var_edge = dec->d_var_edge; a.var_obs = dec->d_var_obs; a.prior = dec->d_prior;
     a.scratch = dec->d_bp_msgs; a.scratch_stride = dec->bp_msgs_per_block;
     a.max_iter = dec->params.bp_max_iter; a.alpha = dec->params.bp_alpha;
-    a.use_shared = dec->d_bp_msgs == nullptr;
+    a.use_shared = dec->d_bp_msgs == nullptr && !dec->cms;
     size_t smem = a.use_shared ? dec->bp_msgs_per_block * 4 : 0;
     const bool osd = dec->params.bp_osd != 0;
     const uint64_t chunk = osd ? 16384 : nshots;       // OSD keeps 8 KB of candidates per unconverged shot
     const int wpl = osd_wpl(dem->DW);
-    const int osd_blocks = dem->num_sms * 2, osd_warps = osd_blocks * 4;
+    int osd_mult = 1;
+    if (const char *env = getenv("GQ_OSD_WARPS")) osd_mult = std::max(1, std::min(8, atoi(env)));
+    const int osd_blocks = dem->num_sms * 2 * osd_mult, osd_warps = osd_blocks * 4;
     const uint32_t osd_kmax = dem->D;
     const size_t osd_stride = (size_t)osd_kmax * (64 * (size_t)wpl + 1);
     if (osd) {
         if (!dec->d_osd_cand) {
             GQ_CUDA(cudaMalloc((void **)&dec->d_osd_cand, chunk * OSD_NCAND * 4));
-            GQ_CUDA(cudaMalloc((void **)&dec->d_osd_fail, (chunk + 2) * 4));   // [0] unconverged count, [1] OSD give-ups, [2..] shots
+            GQ_CUDA(cudaMalloc((void **)&dec->d_osd_fail, (chunk + 4) * 4));   // [0] unconverged count, [1] OSD give-ups, [2] work cursor, [4..] shots
             GQ_CUDA(cudaMalloc((void **)&dec->d_osd_scratch, (size_t)osd_warps * osd_stride * 4));
         }
-        a.osd_k = OSD_NCAND; a.cand = dec->d_osd_cand; a.fail_list = dec->d_osd_fail + 2; a.fail_count = dec->d_osd_fail;
+        a.osd_k = OSD_NCAND; a.cand = dec->d_osd_cand; a.fail_list = dec->d_osd_fail + 4; a.fail_count = dec->d_osd_fail;
     }
     for (uint64_t s0 = 0; s0 < nshots; s0 += chunk) {
         const uint64_t ns = std::min(chunk, nshots - s0);
@@ -726,8 +1071,23 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
         a.flags_out = flags_out ? flags_out + s0 : nullptr;
         a.corr_out = corr_out ? corr_out + s0 * a.MW : nullptr;
         a.nshots = ns;
-        if (osd) GQ_CUDA(cudaMemsetAsync(dec->d_osd_fail, 0, 8, dem->stream));
-        if (a.use_shared) {
+        if (osd) GQ_CUDA(cudaMemsetAsync(dec->d_osd_fail, 0, 16, dem->stream));
+        if (dec->cms) {
+            CmsArgs c;
+            memset(&c, 0, sizeof(c));
+            c.dets = a.dets; c.pred = a.pred; c.iters_out = a.iters_out; c.flags_out = a.flags_out; c.corr_out = a.corr_out;
+            c.nshots = ns; c.D = a.D; c.M = a.M; c.DW = a.DW; c.OW = a.OW; c.MW = a.MW;
+            c.ntiles = dec->cms_ntiles; c.FW = dec->cms_FW; c.SW = dec->cms_SW;
+            memcpy(c.grp_tile, dec->cms_grp_tile, sizeof(c.grp_tile));
+            memcpy(c.grp_word, dec->cms_grp_word, sizeof(c.grp_word));
+            c.tile_var = dec->d_cms_var; c.tile_prior = dec->d_cms_prior;
+            c.tile_obs = dec->d_cms_obs; c.tile_chk = dec->d_cms_chk;
+            c.max_iter = a.max_iter; c.alpha = a.alpha; c.cursor = dec->d_cms_cursor; c.post = dec->d_cms_post;
+            c.osd_k = a.osd_k; c.cand = a.cand; c.fail_list = a.fail_list; c.fail_count = a.fail_count;
+            GQ_CUDA(cudaMemsetAsync(dec->d_cms_cursor, 0, 4, dem->stream));
+            const int blocks = (int)std::min<uint64_t>(ns, (uint64_t)dec->cms_blocks);
+            bp_cms_kernel<<<blocks, dec->cms_threads, dec->cms_smem, dem->stream>>>(c);
+        } else if (a.use_shared) {
             int blocks = (int)std::min<uint64_t>(ns, (uint64_t)dec->bp_blocks);
             bp_kernel<<<blocks, 256, smem, dem->stream>>>(a);
         } else {
@@ -745,7 +1105,8 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
         OsdArgs o;
         memset(&o, 0, sizeof(o));
         o.dets = a.dets; o.pred = a.pred; o.flags_out = a.flags_out; o.corr_out = a.corr_out;
-        o.cand = dec->d_osd_cand; o.fail_list = dec->d_osd_fail + 2; o.nfail = nfail;
+        o.cand = dec->d_osd_cand; o.fail_list = dec->d_osd_fail + 4; o.nfail = nfail; o.cursor = dec->d_osd_fail + 2;
+        o.chk_ptr = dec->d_chk_ptr; o.chk_var = dec->d_chk_var;
         o.kmax = osd_kmax; o.giveups = dec->d_osd_fail + 1;
         o.sentinel = dem->O < 32 ? 0xFFFFFFFFu : 0u;
         o.D = dem->D; o.DW = dem->DW; o.OW = dem->OW; o.MW = a.MW; o.M = dem->M;

@@ -109,6 +109,15 @@ struct gq_dec {
     size_t bp_msgs_per_block = 0;
     int bp_blocks = 0;
     uint32_t bp_nnz = 0;
+    // compressed min-sum kernel (bp.cu: bp_cms_kernel): the Tanner graph as degree-sorted tiles of 32 variables
+    bool cms = false;
+    uint32_t cms_grp_tile[18] = {0}, cms_grp_word[17] = {0};
+    uint32_t *d_cms_var = nullptr, *d_cms_obs = nullptr, *d_cms_cursor = nullptr;
+    float *d_cms_prior = nullptr, *d_cms_post = nullptr;
+    uint16_t *d_cms_chk = nullptr;
+    uint32_t cms_ntiles = 0, cms_FW = 0, cms_SW = 0;
+    size_t cms_smem = 0;
+    int cms_blocks = 0, cms_threads = 0;
     // ---- scratch for gq_collect / gq_decode_b8
     uint32_t *d_dets = nullptr, *d_obs = nullptr, *d_pred = nullptr;
     uint64_t scratch_shots = 0;

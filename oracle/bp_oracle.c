@@ -78,9 +78,10 @@ int orc_bp_minsum(int D, int M, const uint32_t *chk_indptr, const uint32_t *chk_
  * in a basis is unique, the walk may stop at the first moment the syndrome lies in the span of the basis
  * built so far: the later basis columns would get coefficient 0.  max_candidates bounds the walk
  * (0 = all M); max_basis bounds the basis size (0 = D).  max_candidates < 0 is the CUDA kernel's schedule:
- * the first |max_candidates| variables of the reliability order, then EVERY variable in index order (so a
- * syndrome in the column space of H is always reached; the tail is only entered when the reliability-ordered
- * prefix did not suffice).
+ * the first |max_candidates| variables of the reliability order; then, only if they did not suffice, the
+ * variables of the detector that is the lowest bit left of the syndrome, in index order, moving on to the
+ * next such detector whenever that bit changes; and if a detector's variables are used up with its bit still
+ * there, EVERY variable in index order (so a syndrome in the column space of H is always reached).
  * Returns 0 and the error vector on success, 1 if the syndrome was not reached within the bounds. */
 typedef struct { float key; uint32_t idx; } osd_item;
 static int osd_cmp(const void *a, const void *b) {
@@ -131,9 +132,23 @@ int orc_osd0(int D, int M, const uint32_t *chk_indptr, const uint32_t *chk_var, 
         for (int w_ = 0; w_ < CW; ++w_) sc[w_] ^= coef[(size_t)piv[r_] * CW + w_];  \
     }
     REDUCE_S();
-    for (int i = 0; i < max_candidates + tail && !done && nb < max_basis; ++i) {
-        const uint32_t c = i < max_candidates ? items[i].idx : (uint32_t)(i - max_candidates);
-        used = i + 1;
+    int stage = 0, i0 = 0, i2 = 0, tr = -1;
+    uint32_t tk = 0, tend = 0;
+    while (!done && nb < max_basis) {
+        uint32_t c;
+        if (stage == 0) {                           /* the reliability order */
+            if (i0 >= max_candidates) { if (!tail) break; stage = 1; continue; }
+            c = items[i0++].idx;
+        } else if (stage == 1) {                    /* the variables of the lowest detector left of the syndrome */
+            int rs; LOWBIT(s, rs);
+            if (rs != tr) { tr = rs; tk = chk_indptr[tr]; tend = chk_indptr[tr + 1]; }
+            if (tk >= tend) { stage = 2; continue; }
+            c = chk_var[tk++];
+        } else {                                    /* every variable */
+            if (i2 >= M) break;
+            c = (uint32_t)i2++;
+        }
+        ++used;
         memset(v, 0, (size_t)W * 8); memset(vc, 0, (size_t)CW * 8);
         for (uint32_t k = var_indptr[c]; k < var_indptr[c + 1]; ++k) { uint32_t r = edge_chk[var_edge[k]]; v[r >> 6] ^= 1ull << (r & 63); }
         for (;;) {

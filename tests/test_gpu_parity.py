@@ -403,11 +403,13 @@ def _bp_case(name, **params):
 
 
 @pytest.mark.parametrize("name,nshots,scratch", [("rot3", 300, False), ("steane", 300, False), ("rot5", 120, False),
-                                                 ("rot3", 301, True), ("rot5", 123, True), ("toric4", 77, True)])
+                                                 ("rot3", 301, True), ("rot5", 123, True), ("toric4", 77, True),
+                                                 ("rot3", 301, 2), ("steane", 300, 2), ("rot5", 123, 2), ("toric4", 77, 2)])
 def test_bp_matches_oracle_bit_for_bit(name, nshots, scratch):
     """Same schedule, same fp32 summation order as oracle/bp_oracle.c: identical decisions and iteration counts -- for the
-    one-shot-per-block kernel (messages in shared memory) and for the shot-interleaved kernel of the big models
-    (bp_scratch forces it here; ragged shot counts leave its last group of eight partly empty)."""
+    one-shot-per-block kernel (messages in shared memory), for the shot-interleaved kernel (bp_scratch = 1 forces it here;
+    ragged shot counts leave its last group of eight partly empty) and for the compressed min-sum kernel that big models
+    get by default (bp_scratch = 2: check records + one sign bit per edge instead of messages)."""
     dem, demh, bp = _bp_case(name, bp_max_iter=25, bp_alpha=0.9, bp_scratch=scratch)
     orc = po.BpOracle(dem, max_iter=25, alpha=0.9)
     dets, obs = demh.sample(17, 0, nshots)
@@ -431,7 +433,8 @@ def test_bp_matches_oracle_bit_for_bit(name, nshots, scratch):
 
 
 @pytest.mark.parametrize("name,nshots,iters,scratch", [("rot3", 400, 4, False), ("steane", 400, 3, False), ("rot5", 150, 6, False),
-                                                       ("toric4", 150, 8, False), ("steane", 403, 3, True), ("rot5", 149, 6, True)])
+                                                       ("toric4", 150, 8, False), ("steane", 403, 3, True), ("rot5", 149, 6, True),
+                                                       ("steane", 403, 3, 2), ("rot5", 149, 6, 2), ("toric4", 150, 8, 2)])
 def test_bp_osd_matches_oracle_bit_for_bit(name, nshots, iters, scratch):
     """BP (few iterations, so that many shots stay unconverged) + OSD-0: the same error vector as
     oracle/bp_oracle.c::orc_bp_osd0 on every shot, and every solved shot reproduces its syndrome."""

@@ -349,6 +349,99 @@ def test_osd0_oracle_equals_the_textbook_definition():
     assert solved > 100
 
 
+def _osd_kernel_schedule(H, post, syn, prefix):
+    """the CUDA kernel's walk (orc_osd0 with max_candidates = -prefix), restated with python ints: reliability-ordered
+    prefix, then the variables of the lowest detector left of the syndrome, then every variable"""
+    D, M = H.shape
+    cols = [int("".join(str(int(b)) for b in H[::-1, c]), 2) for c in range(M)]
+    order = sorted(range(M), key=lambda v: (float(post[v]), v))[:prefix]
+    rows, piv, chosen = [], {}, []
+    s = int("".join(str(int(b)) for b in syn[::-1]), 2)
+    sm = 0
+    used = 0
+
+    def reduce_s():
+        nonlocal s, sm
+        while s:
+            r = (s & -s).bit_length() - 1
+            if r not in piv:
+                return r
+            s ^= rows[piv[r]][0]; sm ^= rows[piv[r]][1]
+        return -1
+
+    def offer(c):
+        nonlocal used
+        used += 1
+        v, m = cols[c], 0
+        while v:
+            r = (v & -v).bit_length() - 1
+            if r in piv:
+                v ^= rows[piv[r]][0]; m ^= rows[piv[r]][1]
+            else:
+                piv[r] = len(rows); rows.append((v, m | (1 << len(chosen)))); chosen.append(c)
+                return
+
+    rs = reduce_s()
+    for c in order:
+        if rs < 0:
+            break
+        offer(c); rs = reduce_s()
+    tr, k, stage2 = -1, 0, False
+    while rs >= 0 and not stage2:
+        if rs != tr:
+            tr, k = rs, 0
+            row = [c for c in range(M) if H[tr, c]]
+        if k >= len(row):
+            stage2 = True
+            break
+        offer(row[k]); k += 1; rs = reduce_s()
+    if stage2:
+        for c in range(M):
+            if rs < 0:
+                break
+            offer(c); rs = reduce_s()
+    if rs >= 0:
+        return None, used
+    e = np.zeros(M, np.uint8)
+    for b, c in enumerate(chosen):
+        if (sm >> b) & 1:
+            e[c] = 1
+    return e, used
+
+
+def test_osd_kernel_schedule_targets_the_detectors_left_of_the_syndrome():
+    """max_candidates < 0 (the CUDA kernel's walk): when the ordered prefix does not span the syndrome the walk goes on
+    through the variables of the lowest detector still set -- identical to the python restatement above, always a valid
+    correction when one exists, and far fewer candidates than a blind walk through all variables."""
+    from graphqec_b200 import CssCode
+    Hs = np.array([[1, 1, 1, 1, 0, 0, 0], [0, 1, 1, 0, 1, 1, 0], [0, 0, 1, 1, 0, 1, 1]])
+    code = CssCode(Hx=Hs, Hz=Hs, depolarize1_rate=0.01, depolarize2_rate=0.01)
+    code.build_memory_circuit(number_of_rounds=4, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model()
+    H, L = dem.dense_check_matrices()
+    M = dem.num_errors
+    bp = po.BpOracle(dem, max_iter=20)
+    rng = np.random.default_rng(11)
+    import ctypes
+    tail_used = 0
+    for t in range(80):
+        e = (rng.random(M) < 0.03).astype(np.uint8)
+        syn = ((H @ e) % 2).astype(np.uint8)
+        post = rng.normal(0, 3.0, M).astype(np.float32)
+        prefix = int(rng.integers(1, 12))
+        out = np.zeros(M, np.uint8)
+        nb, used = ctypes.c_int(0), ctypes.c_int(0)
+        rc = po.lib().orc_osd0(dem.num_detectors, M, po._p(bp.chk_indptr), po._p(bp.chk_var), po._p(bp.var_indptr), po._p(bp.var_edge),
+                               po._p(post), po._p(syn), -prefix, 0, po._p(out), ctypes.byref(nb), ctypes.byref(used))
+        want, want_used = _osd_kernel_schedule(H, post, syn, prefix)
+        assert (rc == 0) == (want is not None)
+        if want is not None:
+            assert (out == want).all() and (((H @ out) % 2) == syn).all() and used.value == want_used
+            tail_used += used.value > prefix
+            assert used.value < prefix + 8 * int(H.sum(axis=1).max()) + 1 or used.value > M       # targeted, or the full fallback
+    assert tail_used > 40
+
+
 def test_bp_then_osd_always_reproduces_the_syndrome():
     code = RotatedSurfaceCode(distance=3, depolarize1_rate=0.02, depolarize2_rate=0.02)
     code.build_memory_circuit(number_of_rounds=3, logic_check="Z")
