@@ -1,4 +1,4 @@
-// K3b: batched min-sum belief propagation on the DEM Tanner graph, one shot per thread block.
+// K3b: batched min-sum belief propagation on the DEM Tanner graph, one shot (or eight) per thread block.
 //
 // Checks = detectors (D), variables = error mechanisms (M), edges = nnz(H).  Stands in for stimbposd's BP+OSD
 // (reference threshold_lab.py:19,30): min-sum BP as BASELINE.json's north star asks (stimbposd
@@ -6,26 +6,30 @@
 // Flooding schedule, fp32 messages:
 //   check c -> variable v :  alpha * (-1)^{s_c} * prod_{v' != v} sign(m_{v'->c}) * min_{v' != v} |m_{v'->c}|
 //   variable v posterior  :  prior_v + sum_c m_{c->v}      (m_{v->c} = posterior - m_{c->v}, formed on the fly)
-// The block keeps one message per edge (check -> variable) and one posterior per variable; they
-// live in shared memory when the model fits (Steane, small surface codes) and in a per-block
-// HBM/L2 scratch otherwise (rotated d=11: 0.4 MB, BB-144: 1.8 MB per shot).
-// Check update: one warp per check, lanes stride over the check's CSR row; min1 / min2 / argmin /
-// sign parity are combined with warp shuffles, and the same sweep evaluates the parity of the
-// current hard decision, so convergence (H.e == s) costs no extra pass.
-// Summation order and tie rules equal oracle/bp_oracle.c, so results match it bit for bit.
+// Three kernels, one arithmetic (summation order and tie rules equal oracle/bp_oracle.c: results match it bit for bit):
+//  * bp_kernel: the model's messages fit shared memory (Steane, small surface codes): one message per edge + one
+//    posterior per variable in shared memory, check update by one warp per check (min1 / min2 / argmin / sign parity by
+//    warp shuffles; the same sweep evaluates the parity of the hard decision, so convergence costs no extra pass);
+//  * bp_cms_kernel ("compressed min-sum", the default for everything bigger: rotated d = 11, BB-144): NO message in
+//    memory at all -- per check {min1, argmin, min2, sign} and one sign bit per edge, all in shared memory, passes turned
+//    inside out (variables offer their messages to the checks' next records with shared-memory atomics); see there;
+//  * bp_batched_kernel<8>: messages in a global scratch, eight shots interleaved per block (models whose records do not
+//    fit shared memory or with more than 16 detectors per mechanism; params.bp_scratch = 1 forces it).
 //
 // OSD-0 (params.bp_osd; the "OSD" of the reference's decoder="bposd") for the shots BP
 // leaves unconverged, in two steps:
-//  * bp_kernel's epilogue picks the osd_k variables with the smallest posterior LLR, in order (ties by
+//  * the BP kernel's epilogue picks the osd_k variables with the smallest posterior LLR, in order (ties by
 //    index): 4-pass radix select of the k-th key over the block's posterior array, index-ordered
 //    compaction of everything below it, bitonic sort of the k (key, index) pairs in shared memory;
-//  * osd_solve_kernel, one warp per shot, walks those candidates: a column of H joins the basis iff it is
+//  * osd_rref_kernel, one warp per shot, walks those candidates: a column of H joins the basis iff it is
 //    independent of the columns already in it (incremental GF(2) elimination on D-bit vectors spread over
-//    the lanes, pivot = lowest set bit, found with a ballot), and the walk stops the moment the syndrome
+//    the lanes, basis kept fully reduced so that a column is reduced by independent loads instead of a dependent chain),
+//    and the walk stops the moment the syndrome
 //    reduces to zero against the basis -- its representation in a basis is unique, so the later basis
 //    columns of a full OSD-0 would get coefficient 0.  The basis may grow to D columns (rank(H) <= D), and a
-//    shot whose syndrome the osd_k ordered candidates do not span goes on through every variable in index
-//    order, so every syndrome in the column space of H gets a correction; the (impossible for a DEM's own
+//    shot whose syndrome the osd_k ordered candidates do not span goes on through the variables of the detectors left
+//    of its syndrome (then, if need be, through every variable in index
+//    order), so every syndrome in the column space of H gets a correction; the (impossible for a DEM's own
 //    shots) rest is counted and reported as sinter's "discards".  Identical to oracle/bp_oracle.c::orc_osd0
 //    with max_candidates = -osd_k.
 #include <math.h>
@@ -875,6 +879,191 @@ __global__ void __launch_bounds__(128) osd_solve_kernel(OsdArgs a) {
     }
 }
 
+// ---- OSD-0 with a fully reduced basis (the default; osd_solve_kernel above keeps the echelon form and is selected by
+// GQ_OSD_CHAIN=1 for A/B measurements).  The echelon walk reduces a column by a CHAIN of dependent steps -- find the lowest
+// bit, look up its pivot, load that basis vector from L2, XOR, repeat: ~700 cycles per step, ~100 steps per candidate, and
+// one unlucky shot (thousands of candidates against a basis of ~900) holds its warp for a quarter of a second.  Here every
+// basis vector is kept zero at all OTHER pivots, so a raw column is reduced in ONE step: the vectors of the pivots among
+// its <= ~10 detectors, all loads independent and in flight together; what is left is zero (dependent) or a new basis
+// vector, whose pivot bit is then cleared from the earlier vectors that carry it (about half of them; independent
+// read-modify-writes, eight in flight).  Each vector travels with its composition in basis columns (one bit per ordinal,
+// only the words in use are touched), so the syndrome's composition is the answer with no back-substitution.
+// Same candidates in the same order, same independence decisions (those do not depend on the form of the basis), same
+// unique solution as oracle/bp_oracle.c::orc_osd0 -- including the detector the targeted stage looks at: the lowest bit
+// left of the syndrome is the same for every echelon basis of the same span.
+template <int WPL>
+__global__ void __launch_bounds__(128) osd_rref_kernel(OsdArgs a) {
+    extern __shared__ uint16_t piv_all[];
+    constexpr int NB = WPL <= 2 ? 8 : (WPL == 4 ? 4 : 2);     // rows in flight per batch
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint16_t *piv = piv_all + (size_t)wib * ((a.D + 1) & ~1u);
+    uint32_t *basis = a.scratch + (size_t)warp * a.scratch_stride;
+    uint32_t *coef = basis + (size_t)a.kmax * 32 * WPL;
+    uint32_t *col = coef + (size_t)a.kmax * 32 * WPL;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(a.cursor, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= a.nfail) break;
+        const uint32_t shot = a.fail_list[item];
+        const uint32_t *cand = a.cand + (size_t)item * OSD_NCAND;
+        for (uint32_t r = lane; r < a.D; r += 32) piv[r] = 0xFFFFu;
+        uint32_t s[WPL], sc[WPL];
+#pragma unroll
+        for (int j = 0; j < WPL; ++j) {
+            const uint32_t w = j * 32 + lane;
+            uint32_t word = w < a.DW ? a.dets[(size_t)shot * a.DW + w] : 0u;
+            if (w == a.DW - 1 && (a.D & 31)) word &= (1u << (a.D & 31)) - 1u;
+            s[j] = word;
+            sc[j] = 0u;
+        }
+        __syncwarp();
+        int nb = 0;
+        int rs = osd_lowbit<WPL>(s, lane);          // lowest bit left of the syndrome (never a pivot), -1 = solved
+        int stage = 0, tr = -1;
+        uint32_t i0 = 0, tk = 0, tend = 0, i2 = 0;
+        while (rs >= 0 && nb < (int)a.kmax) {
+            uint32_t c;
+            if (stage == 0) {
+                if (i0 >= OSD_NCAND) { stage = 1; continue; }
+                c = cand[i0++];
+                if (c == 0xFFFFFFFFu) continue;
+            } else if (stage == 1) {
+                if (tr != rs) { tr = rs; tk = a.chk_ptr[tr]; tend = a.chk_ptr[tr + 1]; }
+                if (tk >= tend) { stage = 2; continue; }
+                c = a.chk_var[tk++];
+            } else {
+                if (i2 >= a.M) break;
+                c = i2++;
+            }
+            // ---- the column, minus the basis vectors of the pivots among its detectors
+            uint32_t v[WPL], vc[WPL];
+#pragma unroll
+            for (int j = 0; j < WPL; ++j) { v[j] = 0u; vc[j] = 0u; }
+            const uint32_t cw = (uint32_t)(nb + 31) >> 5;           // composition words in use
+            const uint32_t k0 = a.var_ptr[c], k1 = a.var_ptr[c + 1];
+            for (uint32_t kk = k0; kk < k1; kk += 32) {
+                const uint32_t k = kk + lane;
+                const uint32_t d = k < k1 ? a.var_chk[k] : 0xFFFFFFFFu;
+                const uint32_t pm = k < k1 ? (uint32_t)piv[d] : 0xFFFFu;
+                const int cnt = (int)min(32u, k1 - kk);
+                for (int t = 0; t < cnt; ++t) {
+                    const uint32_t dd = __shfl_sync(0xffffffffu, d, t), w = dd >> 5;
+#pragma unroll
+                    for (int j = 0; j < WPL; ++j)
+                        if ((int)(w >> 5) == j && (int)(w & 31u) == lane) v[j] ^= 1u << (dd & 31u);
+                }
+                unsigned m = __ballot_sync(0xffffffffu, pm != 0xFFFFu);
+                while (m) {
+                    uint32_t pp[NB];
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        pp[q] = 0xFFFFu;
+                        if (m) { const int l = __ffs(m) - 1; m &= m - 1; pp[q] = __shfl_sync(0xffffffffu, pm, l); }
+                    }
+                    uint32_t rb[NB][WPL], rc[NB][WPL];
+#pragma unroll
+                    for (int q = 0; q < NB; ++q)
+#pragma unroll
+                        for (int j = 0; j < WPL; ++j) {
+                            const bool on = pp[q] != 0xFFFFu;
+                            rb[q][j] = on ? basis[((size_t)pp[q] * WPL + j) * 32 + lane] : 0u;
+                            rc[q][j] = (on && (uint32_t)(j * 32 + lane) < cw) ? coef[((size_t)pp[q] * WPL + j) * 32 + lane] : 0u;
+                        }
+#pragma unroll
+                    for (int q = 0; q < NB; ++q)
+#pragma unroll
+                        for (int j = 0; j < WPL; ++j) { v[j] ^= rb[q][j]; vc[j] ^= rc[q][j]; }
+                }
+            }
+            const int r = osd_lowbit<WPL>(v, lane);
+            if (r < 0) continue;                                    // dependent on the basis: skipped
+            // ---- joins the basis as ordinal nb, pivot r: clear bit r from the earlier vectors
+#pragma unroll
+            for (int j = 0; j < WPL; ++j)
+                if ((nb >> 10) == j && lane == ((nb >> 5) & 31)) vc[j] |= 1u << (nb & 31);
+            const uint32_t wr = (uint32_t)r >> 5, jr = wr >> 5, lr = wr & 31u, bitr = 1u << (r & 31);
+            const uint32_t cw1 = ((uint32_t)nb >> 5) + 1u;          // composition words in use, own bit included
+            for (int base = 0; base < nb; base += 32) {
+                const int i = base + lane;
+                const bool has = i < nb && (basis[((size_t)i * WPL + jr) * 32 + lr] & bitr);
+                unsigned m = __ballot_sync(0xffffffffu, has);
+                while (m) {
+                    int idx[NB];
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) {
+                        idx[q] = -1;
+                        if (m) { idx[q] = base + __ffs(m) - 1; m &= m - 1; }
+                    }
+                    uint32_t rb[NB][WPL], rc[NB][WPL];
+                    // v is zero below word wr, and the compositions beyond word cw1: those words are left alone
+#pragma unroll
+                    for (int q = 0; q < NB; ++q)
+#pragma unroll
+                        for (int j = 0; j < WPL; ++j) {
+                            const uint32_t w = (uint32_t)(j * 32 + lane);
+                            rb[q][j] = (idx[q] >= 0 && w >= wr) ? basis[((size_t)idx[q] * WPL + j) * 32 + lane] : 0u;
+                            rc[q][j] = (idx[q] >= 0 && w < cw1) ? coef[((size_t)idx[q] * WPL + j) * 32 + lane] : 0u;
+                        }
+#pragma unroll
+                    for (int q = 0; q < NB; ++q)
+#pragma unroll
+                        for (int j = 0; j < WPL; ++j) {
+                            const uint32_t w = (uint32_t)(j * 32 + lane);
+                            if (idx[q] >= 0 && w >= wr) basis[((size_t)idx[q] * WPL + j) * 32 + lane] = rb[q][j] ^ v[j];
+                            if (idx[q] >= 0 && w < cw1) coef[((size_t)idx[q] * WPL + j) * 32 + lane] = rc[q][j] ^ vc[j];
+                        }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < WPL; ++j) {
+                basis[((size_t)nb * WPL + j) * 32 + lane] = v[j];
+                coef[((size_t)nb * WPL + j) * 32 + lane] = vc[j];   // all words: the scratch still holds the previous shot's
+            }
+            if (lane == 0) { piv[r] = (uint16_t)nb; col[nb] = c; }
+            ++nb;
+            __syncwarp();
+            // ---- the syndrome: only its bit r can have become reducible
+            uint32_t wv = 0;
+#pragma unroll
+            for (int j = 0; j < WPL; ++j) if ((int)jr == j) wv = s[j];
+            if (__shfl_sync(0xffffffffu, wv, (int)lr) & bitr) {
+#pragma unroll
+                for (int j = 0; j < WPL; ++j) { s[j] ^= v[j]; sc[j] ^= vc[j]; }
+                rs = osd_lowbit<WPL>(s, lane);
+            }
+        }
+        if (rs < 0) {
+            // the error vector = the basis columns whose bit is set in the syndrome's composition
+            uint32_t *corr_row = a.corr_out ? a.corr_out + (size_t)shot * a.MW : nullptr;
+            if (corr_row) for (uint32_t w = lane; w < a.MW; w += 32) corr_row[w] = 0u;
+            __syncwarp();
+            uint32_t om = 0;
+#pragma unroll
+            for (int j = 0; j < WPL; ++j) {
+                uint32_t bits = sc[j];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const uint32_t c = col[((j * 32 + lane) << 5) + b];
+                    om ^= a.var_obs[c];
+                    if (corr_row) atomicXor(&corr_row[c >> 5], 1u << (c & 31u));
+                }
+            }
+            om = __reduce_xor_sync(0xffffffffu, om);
+            if (lane == 0) {
+                a.pred[(size_t)shot * a.OW] = om;
+                if (a.flags_out) a.flags_out[shot] = 0;
+            }
+        } else if (lane == 0) {
+            atomicAdd(a.giveups, 1u);
+            if (a.sentinel) a.pred[(size_t)shot * a.OW] = a.sentinel;
+        }
+        __syncwarp();
+    }
+}
+
 static int osd_wpl(uint32_t DW) { return DW <= 32 ? 1 : (DW <= 64 ? 2 : (DW <= 128 ? 4 : (DW <= 256 ? 8 : 0))); }
 
 int gq_bp_create(gq_dec *dec) {
@@ -928,6 +1117,10 @@ int gq_bp_create(gq_dec *dec) {
         cudaFuncSetAttribute(osd_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
         cudaFuncSetAttribute(osd_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
         cudaFuncSetAttribute(osd_solve_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
+        cudaFuncSetAttribute(osd_rref_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
+        cudaFuncSetAttribute(osd_rref_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
+        cudaFuncSetAttribute(osd_rref_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
+        cudaFuncSetAttribute(osd_rref_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem);
     }
     GQ_CUDA(cudaMalloc((void **)&dec->d_prior, (size_t)M * 4));
     GQ_CUDA(cudaMemcpy(dec->d_prior, prior.data(), (size_t)M * 4, cudaMemcpyHostToDevice));
@@ -1049,7 +1242,8 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
     a.use_shared = dec->d_bp_msgs == nullptr && !dec->cms;
     size_t smem = a.use_shared ? dec->bp_msgs_per_block * 4 : 0;
     const bool osd = dec->params.bp_osd != 0;
-    const uint64_t chunk = osd ? 16384 : nshots;       // OSD keeps 8 KB of candidates per unconverged shot
+    const uint64_t chunk = osd ? 32768 : nshots;       // OSD keeps 8 KB of candidates per unconverged shot; the OSD kernel ends with its
+                                                        // longest walk, so bigger chunks amortise that tail (8192 shots 3.7e4/s, 16384 4.3e4/s)
     const int wpl = osd_wpl(dem->DW);
     int osd_mult = 1;
     if (const char *env = getenv("GQ_OSD_WARPS")) osd_mult = std::max(1, std::min(8, atoi(env)));
@@ -1114,11 +1308,21 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
         o.scratch = dec->d_osd_scratch; o.scratch_stride = osd_stride;
         const int ob = (int)std::min<uint32_t>((nfail + 3) / 4, (uint32_t)osd_blocks);
         const size_t osmem = 4 * (size_t)((dem->D + 1) & ~1u) * 2;
-        switch (wpl) {
-        case 1: osd_solve_kernel<1><<<ob, 128, osmem, dem->stream>>>(o); break;
-        case 2: osd_solve_kernel<2><<<ob, 128, osmem, dem->stream>>>(o); break;
-        case 4: osd_solve_kernel<4><<<ob, 128, osmem, dem->stream>>>(o); break;
-        default: osd_solve_kernel<8><<<ob, 128, osmem, dem->stream>>>(o); break;
+        static const bool chain = getenv("GQ_OSD_CHAIN") != nullptr;      // A/B: the echelon-form walk
+        if (chain) {
+            switch (wpl) {
+            case 1: osd_solve_kernel<1><<<ob, 128, osmem, dem->stream>>>(o); break;
+            case 2: osd_solve_kernel<2><<<ob, 128, osmem, dem->stream>>>(o); break;
+            case 4: osd_solve_kernel<4><<<ob, 128, osmem, dem->stream>>>(o); break;
+            default: osd_solve_kernel<8><<<ob, 128, osmem, dem->stream>>>(o); break;
+            }
+        } else {
+            switch (wpl) {
+            case 1: osd_rref_kernel<1><<<ob, 128, osmem, dem->stream>>>(o); break;
+            case 2: osd_rref_kernel<2><<<ob, 128, osmem, dem->stream>>>(o); break;
+            case 4: osd_rref_kernel<4><<<ob, 128, osmem, dem->stream>>>(o); break;
+            default: osd_rref_kernel<8><<<ob, 128, osmem, dem->stream>>>(o); break;
+            }
         }
         GQ_CUDA(cudaGetLastError());
         ++*launches;

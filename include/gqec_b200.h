@@ -52,8 +52,9 @@ typedef struct gq_decoder_params {
     int32_t legacy_tiers;      /* matching: 1 = skip the first tier (A/B testing only) */
     int32_t bp_osd;            /* BP: 1 = order-0 ordered-statistics decoding (OSD-0) of the shots BP leaves
                                   unconverged -- the "OSD" of the reference's decoder="bposd" (stimbposd) */
-    int32_t bp_scratch;        /* BP: 1 = use the global-scratch (shot-interleaved) kernel even when the messages would fit
-                                  shared memory (tests) */
+    int32_t bp_scratch;        /* BP kernel choice (tests, A/B): 0 = automatic (messages in shared memory when the model fits,
+                                  else the compressed min-sum kernel, else the global-scratch kernel), 1 = force the
+                                  global-scratch (shot-interleaved) kernel, 2 = force the compressed min-sum kernel */
     int32_t reserved[5];
 } gq_decoder_params;
 
