@@ -1280,6 +1280,8 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
             c.osd_k = a.osd_k; c.cand = a.cand; c.fail_list = a.fail_list; c.fail_count = a.fail_count;
             GQ_CUDA(cudaMemsetAsync(dec->d_cms_cursor, 0, 4, dem->stream));
             const int blocks = (int)std::min<uint64_t>(ns, (uint64_t)dec->cms_blocks);
+            // the limit is per function, not per decoder: another decoder of this process may have set a smaller one
+            GQ_CUDA(cudaFuncSetAttribute(bp_cms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec->cms_smem));
             bp_cms_kernel<<<blocks, dec->cms_threads, dec->cms_smem, dem->stream>>>(c);
         } else if (a.use_shared) {
             int blocks = (int)std::min<uint64_t>(ns, (uint64_t)dec->bp_blocks);
@@ -1309,6 +1311,11 @@ int gq_bp_decode(gq_dec *dec, const uint32_t *dets_sm, uint64_t nshots, uint32_t
         const int ob = (int)std::min<uint32_t>((nfail + 3) / 4, (uint32_t)osd_blocks);
         const size_t osmem = 4 * (size_t)((dem->D + 1) & ~1u) * 2;
         static const bool chain = getenv("GQ_OSD_CHAIN") != nullptr;      // A/B: the echelon-form walk
+        {   // per-function limit (see above)
+            const void *fn = chain ? (wpl == 1 ? (const void *)osd_solve_kernel<1> : wpl == 2 ? (const void *)osd_solve_kernel<2> : wpl == 4 ? (const void *)osd_solve_kernel<4> : (const void *)osd_solve_kernel<8>)
+                                   : (wpl == 1 ? (const void *)osd_rref_kernel<1> : wpl == 2 ? (const void *)osd_rref_kernel<2> : wpl == 4 ? (const void *)osd_rref_kernel<4> : (const void *)osd_rref_kernel<8>);
+            GQ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osmem));
+        }
         if (chain) {
             switch (wpl) {
             case 1: osd_solve_kernel<1><<<ob, 128, osmem, dem->stream>>>(o); break;
