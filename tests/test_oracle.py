@@ -456,3 +456,157 @@ def test_bp_then_osd_always_reproduces_the_syndrome():
         assert st in (-1, 0) and (((H @ e) % 2) == bits[s]).all()
         used += st == 0
     assert used > 10
+
+
+# ------------------------------------------------------------------------------------------
+# The two reformulations the big-model GPU kernels rely on, restated in python and held against the oracle on the CPU
+# (the kernels themselves are compared with the oracle bit for bit in tests/test_gpu_parity.py)
+# ------------------------------------------------------------------------------------------
+
+def _compressed_min_sum(dem, syn, max_iter, alpha):
+    """bp_cms_kernel's formulation: no per-edge message is stored -- per check (min1, argmin, min2, sign) and one sign bit
+    per edge; a variable rebuilds its incoming messages from its checks' records, and offers its outgoing ones to the
+    checks' next records.  fp32, the sums in ascending check order."""
+    f32 = np.float32
+    D, M = dem.num_detectors, dem.num_errors
+    ptr, idx = dem.det_indptr.astype(int), dem.det_idx.astype(int)
+    p = np.clip(dem.probs, 1e-30, 1 - 1e-7)
+    prior = np.log((1 - p) / p).astype(f32)
+    alpha = f32(alpha)
+    m1o, m2o, argo, sgo = np.zeros(D, f32), np.zeros(D, f32), np.zeros(D, int), np.zeros(D, int)
+    esign = {}
+    for it in range(1, max_iter + 2):
+        m1n, m2n = np.full(D, np.inf, f32), np.full(D, np.inf, f32)
+        argn, sgn, par = np.full(D, -1, int), np.zeros(D, int), np.zeros(D, int)
+        dec = np.zeros(M, np.uint8)
+        for v in range(M):
+            cs = sorted(idx[ptr[v]:ptr[v + 1]])
+            tot, cv = prior[v], []
+            for c in cs:
+                mag = m2o[c] if argo[c] == v else m1o[c]
+                cv.append(f32(alpha * (f32(-mag) if sgo[c] ^ esign.get((v, c), 0) else mag)))
+            for x in cv:
+                tot = f32(tot + x)
+            bit = int(tot < 0)
+            dec[v] = bit
+            for c, x in zip(cs, cv):
+                m = f32(tot - x)
+                neg = int(m < 0)
+                esign[(v, c)] = neg
+                sgn[c] ^= neg
+                par[c] ^= bit
+                a = abs(m)
+                if a < m1n[c] or (a == m1n[c] and v < argn[c]):
+                    m2n[c] = m1n[c]; m1n[c] = a; argn[c] = v
+                elif a < m2n[c]:
+                    m2n[c] = a
+        bad = (par != syn).any()
+        m1o, m2o, argo, sgo = m1n, m2n, argn, sgn ^ syn
+        if it > 1 and not bad:
+            return dec, it - 1
+    return dec, -max_iter
+
+
+def test_compressed_min_sum_equals_the_flooding_schedule():
+    code = RotatedSurfaceCode(distance=3, depolarize1_rate=0.01, depolarize2_rate=0.01)
+    code.build_memory_circuit(number_of_rounds=3, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model()
+    H, L = dem.dense_check_matrices()
+    orc = po.BpOracle(dem, max_iter=12, alpha=0.9)
+    rng = np.random.default_rng(5)
+    iters = set()
+    for s in range(40):
+        e = (rng.random(dem.num_errors) < np.clip(dem.probs * 3, 0, 0.5)).astype(np.uint8)
+        syn = ((H @ e) % 2).astype(np.uint8)
+        want, it = orc.decode(syn)
+        got, it2 = _compressed_min_sum(dem, syn, 12, 0.9)
+        assert it == it2 and (want == got).all()
+        iters.add(it)
+    assert len(iters) >= 4 and min(iters) < 0          # converged after different numbers of iterations, and not at all
+
+
+def _osd_fully_reduced(H, post, syn, prefix):
+    """osd_rref_kernel's formulation of the kernel schedule: the basis is kept zero at all other pivots, a column is
+    reduced in one step by the vectors of the pivots among its own detectors, compositions are kept in basis columns."""
+    D, M = H.shape
+    cols = [int("".join(str(int(b)) for b in H[::-1, c]), 2) for c in range(M)]
+    order = sorted(range(M), key=lambda v: (float(post[v]), v))[:prefix]
+    rows, coefs, piv, chosen = [], [], {}, []
+    state = {"s": int("".join(str(int(b)) for b in syn[::-1]), 2), "sc": 0, "used": 0}
+    low = lambda x: (x & -x).bit_length() - 1 if x else -1
+
+    def offer(c):
+        state["used"] += 1
+        v, vc, h = cols[c], 0, cols[c]
+        while h:
+            d = low(h); h &= h - 1
+            if d in piv:
+                v ^= rows[piv[d]]; vc ^= coefs[piv[d]]
+        assert all(((v >> d) & 1) == 0 for d in piv)          # one step suffices
+        if v == 0:
+            return
+        r, nb = low(v), len(rows)
+        vc |= 1 << nb
+        for i in range(nb):
+            if (rows[i] >> r) & 1:
+                rows[i] ^= v; coefs[i] ^= vc
+        rows.append(v); coefs.append(vc); piv[r] = nb; chosen.append(c)
+        if (state["s"] >> r) & 1:
+            state["s"] ^= v; state["sc"] ^= vc
+
+    for c in order:
+        if state["s"] == 0:
+            break
+        offer(c)
+    tr, k, row, stage2 = -1, 0, [], False
+    while state["s"]:
+        rs = low(state["s"])
+        if rs != tr:
+            tr, k, row = rs, 0, [c for c in range(M) if H[rs, c]]
+        if k >= len(row):
+            stage2 = True
+            break
+        offer(row[k]); k += 1
+    if stage2:
+        for c in range(M):
+            if state["s"] == 0:
+                break
+            offer(c)
+    if state["s"]:
+        return None, state["used"]
+    e = np.zeros(M, np.uint8)
+    for b, c in enumerate(chosen):
+        if (state["sc"] >> b) & 1:
+            e[c] = 1
+    return e, state["used"]
+
+
+def test_fully_reduced_osd_equals_the_echelon_walk():
+    """same candidates, same independence decisions, same detector targeted by the walk past the prefix (the lowest bit
+    left of the syndrome does not depend on the form of the basis), same unique solution"""
+    import ctypes
+    from graphqec_b200 import CssCode
+    Hs = np.array([[1, 1, 1, 1, 0, 0, 0], [0, 1, 1, 0, 1, 1, 0], [0, 0, 1, 1, 0, 1, 1]])
+    code = CssCode(Hx=Hs, Hz=Hs, depolarize1_rate=0.01, depolarize2_rate=0.01)
+    code.build_memory_circuit(number_of_rounds=4, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model()
+    H, L = dem.dense_check_matrices()
+    M = dem.num_errors
+    bp = po.BpOracle(dem, max_iter=20)
+    rng = np.random.default_rng(3)
+    tails = 0
+    for t in range(120):
+        e = (rng.random(M) < 0.03).astype(np.uint8)
+        syn = ((H @ e) % 2).astype(np.uint8)
+        post = rng.normal(0, 3.0, M).astype(np.float32)
+        prefix = int(rng.integers(1, 40))
+        out = np.zeros(M, np.uint8)
+        nb, used = ctypes.c_int(0), ctypes.c_int(0)
+        rc = po.lib().orc_osd0(dem.num_detectors, M, po._p(bp.chk_indptr), po._p(bp.chk_var), po._p(bp.var_indptr), po._p(bp.var_edge),
+                               po._p(post), po._p(syn), -prefix, 0, po._p(out), ctypes.byref(nb), ctypes.byref(used))
+        want, want_used = _osd_fully_reduced(H, post, syn, prefix)
+        assert (rc == 0) == (want is not None)
+        if want is not None:
+            assert (out == want).all() and used.value == want_used
+        tails += used.value > prefix
+    assert tails > 60
