@@ -647,6 +647,34 @@ def test_bb144_at_p3e3_every_shot_gets_a_valid_correction():
     osd.close(); demh.close()
 
 
+def test_bb144_bp_and_osd_equal_the_oracle_shot_by_shot():
+    """BASELINE configs[4] at full size through the kernels big models get (compressed min-sum BP; OSD-0 with the fully
+    reduced basis on two words per lane): the same BP iteration counts and the same error vectors as
+    oracle/bp_oracle.c::orc_bp_osd0 (kernel schedule), bit for bit, on a sample of shots at p = 3e-3 -- where almost every
+    shot goes through OSD."""
+    code = gq.BivariateBicycleCode(depolarize1_rate=0.003, depolarize2_rate=0.003)
+    code.build_memory_circuit(number_of_rounds=12, logic_check="Z")
+    dem = code.memory_circuit.detector_error_model()
+    demh = be.DemHandle(dem, device=0)
+    osd = be.DecoderHandle(demh, be.BP_MINSUM, bp_max_iter=30, bp_alpha=0.9, bp_osd=True)
+    orc = po.BpOracle(dem, max_iter=30, alpha=0.9)
+    n = 48
+    dets, obs = demh.sample(13, 0, n)
+    pred, it_gpu, flags, corr = osd.decode(dets, want_weights=True, want_flags=True, want_corrections=True)
+    bits = np.unpackbits(b8(dets, dem.num_detectors), axis=1, bitorder="little")[:, : dem.num_detectors]
+    cb = np.unpackbits(corr.cpu().numpy().view(np.uint8).reshape(n, -1), axis=1, bitorder="little")[:, : dem.num_errors]
+    it_gpu, flags = it_gpu.cpu().numpy(), flags.cpu().numpy()
+    n_osd = 0
+    for s in range(n):
+        e, it, st, nb, used = orc.decode_osd(bits[s], max_candidates=-2048)
+        assert it == it_gpu[s], (s, it, it_gpu[s])
+        assert st != 1 and flags[s] == 0
+        assert (e == cb[s]).all(), (s, it, st, nb, used)
+        n_osd += st == 0
+    assert n_osd >= n // 2
+    osd.close(); demh.close()
+
+
 @pytest.mark.parametrize("kind,d,p,nshots", [("UnrotatedSurfaceCode", 15, 0.003, 160), ("RotatedSurfaceCode", 17, 0.005, 96)])
 def test_large_codes_match_the_oracle(kind, d, p, nshots):
     """BASELINE configs[2] (unrotated d = 15, 15 rounds: 6300 detectors, ~270 defects per shot) and a d = 17 point of the
