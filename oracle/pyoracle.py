@@ -43,6 +43,7 @@ def lib() -> ctypes.CDLL:
         c = ctypes
         L.orc_max_weight_matching.restype = c.c_longlong
         L.orc_max_weight_matching.argtypes = [c.c_int, c.c_void_p, c.c_void_p]
+        L.orc_set_jump_start.argtypes = [c.c_int]
         L.orc_graph_create.restype = c.c_void_p
         L.orc_graph_create.argtypes = [c.c_int, c.c_int, c.c_int] + [c.c_void_p] * 4
         L.orc_graph_free.argtypes = [c.c_void_p]
@@ -203,6 +204,13 @@ def count_errors(pred: np.ndarray, obs: np.ndarray) -> int:
     pred = np.ascontiguousarray(pred, dtype=np.uint8).reshape(len(obs), -1)
     obs = np.ascontiguousarray(obs, dtype=np.uint8)
     return int(lib().orc_count_errors(_p(pred), _p(obs), len(obs), obs.shape[1]))
+
+
+def set_jump_start(on: bool) -> None:
+    """Process-wide switch of the blossom solver's greedy dual-feasible start (``mwpm_oracle.c::blossom_solve``): same
+    optimum weight, ~4x fewer phases.  Off by default -- every parity check runs the plain textbook schedule; ``bench.py``
+    turns it on for the timed CPU baseline so that the baseline is not handicapped."""
+    lib().orc_set_jump_start(1 if on else 0)
 
 
 def collect(dem, seed: int, nshots: int, nthreads: int = 1, oracle: MwpmOracle | None = None, chunk: int = 20000):

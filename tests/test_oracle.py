@@ -610,3 +610,30 @@ def test_fully_reduced_osd_equals_the_echelon_walk():
             assert (out == want).all() and used.value == want_used
         tails += used.value > prefix
     assert tails > 60
+
+
+def test_jump_start_reaches_the_same_optimum():
+    """The blossom port's optional greedy start (used only for the timed CPU baseline) changes the schedule, not the
+    answer: same total weight on random dense graphs (ties included) and on surface-code shots, same failure count."""
+    rng = np.random.default_rng(1)
+    L = po.lib()
+    try:
+        for t in range(150):
+            n = 2 * int(rng.integers(1, 20))
+            w = rng.integers(1, 4 if t % 3 == 0 else 60, size=(n, n)).astype(np.int64)
+            w = np.triu(w, 1); w = w + w.T
+            ww = np.where(np.eye(n, dtype=bool), 0, (w.max() + 1) * (n + 2) - w).astype(np.int64)
+            po.set_jump_start(False); t0, m0 = po.max_weight_matching(ww)
+            po.set_jump_start(True); t1, m1 = po.max_weight_matching(ww)
+            assert t0 == t1 and (np.asarray(m1) >= 0).all() and all(m1[m1[i]] == i for i in range(n))
+        code = RotatedSurfaceCode(distance=5, depolarize1_rate=0.008, depolarize2_rate=0.008)
+        code.build_memory_circuit(number_of_rounds=5, logic_check="Z")
+        dem = code.memory_circuit.detector_error_model(decompose_errors=True)
+        orc = po.MwpmOracle(dem)
+        dets, obs = po.sample(dem, 21, 3000)
+        po.set_jump_start(False); p0, w0 = orc.decode_batch(dets, nthreads=2, return_weights=True)
+        po.set_jump_start(True); p1, w1 = orc.decode_batch(dets, nthreads=2, return_weights=True)
+        assert (w0 == w1).all() and w0.max() > 0
+        assert (p0 != p1).sum() <= 3                                  # equal-weight optima of different parity are rare
+    finally:
+        po.set_jump_start(False)
