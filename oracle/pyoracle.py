@@ -215,17 +215,24 @@ def set_jump_start(on: bool) -> None:
 
 def collect(dem, seed: int, nshots: int, nthreads: int = 1, oracle: MwpmOracle | None = None, chunk: int = 20000):
     """CPU restatement of the whole path: sample -> decode (exact MWPM) -> count."""
+    import concurrent.futures as cf
+
     oracle = oracle or MwpmOracle(dem)
     errors = 0
     done = 0
-    k = 0
+    sizes = []
     while done < nshots:
-        n = min(chunk, nshots - done)
-        dets, obs = sample(dem, seed + 7919 * k, n)
-        pred = oracle.decode_batch(dets, nthreads=nthreads)
-        errors += count_errors(pred, obs)
-        done += n
-        k += 1
+        sizes.append(min(chunk, nshots - done))
+        done += sizes[-1]
+    # the (single-threaded) sampler of chunk k + 1 runs beside the (multi-threaded) decoder of chunk k: same chunks, same
+    # seeds, same result as the plain loop -- the serial sampler just stops costing the multi-threaded baseline wall time
+    with cf.ThreadPoolExecutor(1) as ex:
+        nxt = ex.submit(sample, dem, seed, sizes[0]) if sizes else None
+        for k, n in enumerate(sizes):
+            dets, obs = nxt.result()
+            nxt = ex.submit(sample, dem, seed + 7919 * (k + 1), sizes[k + 1]) if k + 1 < len(sizes) else None
+            pred = oracle.decode_batch(dets, nthreads=nthreads)
+            errors += count_errors(pred, obs)
     return done, errors
 
 
